@@ -1,0 +1,87 @@
+"""Binary layouts of the records that cross the C-ABI (``include/dspi_b200.h``).
+
+They are byte-for-byte the reference firmware's records so that host configs
+drop in unchanged (reference: ``firmware/DSPi/config.h:383-453``,
+``crossfeed.h:26-59``, ``leveller.h:59-136``, ``loudness.h:11-23``).  Sizes are
+asserted here, in the C header, and against the compiled reference in
+``tests/test_oracle_vs_ref.py``.
+"""
+import numpy as np
+
+MAX_BANDS = 12          # config.h:329  (storage stride of filters[][])
+NUM_BANDS = 10          # dsp_pipeline.c:36-44 channel_band_counts
+LA_SAMPLES = 480        # leveller.h:36
+LOUD_STEPS = 61         # loudness.h:7
+
+FLAT, PEAKING, LOWSHELF, HIGHSHELF, LOWPASS, HIGHPASS = range(6)   # config.h:440-443
+
+_f = np.float32
+_i = np.int32
+_u = np.uint32
+_b = np.uint8
+
+# config.h:418-431 — RP2350 Biquad (68 bytes)
+BIQUAD_F32 = np.dtype({
+    "names": ["b0", "b1", "b2", "a1", "a2", "s1", "s2", "sva1", "sva2", "sva3",
+              "svm0", "svm1", "svm2", "svic1eq", "svic2eq", "svf_type", "use_svf", "bypass"],
+    "formats": [_f] * 15 + [_u, _b, _b],
+    "offsets": [0, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 44, 48, 52, 56, 60, 64, 65],
+    "itemsize": 68})
+
+# config.h:433-437, dsp_process_rp2040.S:6-14 — RP2040 Biquad (32 bytes)
+BIQUAD_Q28 = np.dtype({
+    "names": ["b0", "b1", "b2", "a1", "a2", "s1", "s2", "bypass"],
+    "formats": [_i] * 7 + [_b],
+    "offsets": [0, 4, 8, 12, 16, 20, 24, 28],
+    "itemsize": 32})
+
+# config.h:445-453 — EqParamPacket (packed, 16 bytes)
+EQ_PARAM = np.dtype({
+    "names": ["channel", "band", "type", "reserved", "freq", "Q", "gain_db"],
+    "formats": [_b, _b, _b, _b, _f, _f, _f],
+    "offsets": [0, 1, 2, 3, 4, 8, 12],
+    "itemsize": 16})
+
+# config.h:383-389 / 392-400 (packed)
+CROSSPOINT = np.dtype({
+    "names": ["enabled", "phase_invert", "gain_db", "gain_linear"],
+    "formats": [_b, _b, _f, _f], "offsets": [0, 1, 4, 8], "itemsize": 12})
+OUTPUT = np.dtype({
+    "names": ["enabled", "mute", "gain_db", "gain_linear", "delay_ms", "delay_samples"],
+    "formats": [_b, _b, _f, _f, _f, _i], "offsets": [0, 1, 4, 8, 12, 16], "itemsize": 20})
+
+# crossfeed.h:46-59 — CrossfeedState (28 bytes)
+XFEED_F32 = np.dtype([(n, _f) for n in
+                      ("lp_a0", "lp_b1", "lp_state_L", "lp_state_R", "ap_a", "ap_state_L", "ap_state_R")])
+XFEED_Q28 = np.dtype([(n, _i) for n in
+                      ("lp_a0", "lp_b1", "lp_state_L", "lp_state_R", "ap_a", "ap_state_L", "ap_state_R")])
+
+# leveller.h:81-99 — LevellerCoeffs (36 bytes)
+LEV_COEFFS = np.dtype([(n, _f) for n in
+                       ("alpha_rms", "alpha_attack", "alpha_release", "threshold_db", "ratio",
+                        "knee_width_db", "makeup_db", "gate_threshold_db", "max_gain_db")])
+# leveller.h:107-136 — LevellerState (3864 bytes)
+LEV_STATE_F32 = np.dtype([("env_sq_l", _f), ("env_sq_r", _f), ("gain_smooth_db", _f),
+                          ("gain_linear", _f), ("gain_prev_linear", _f),
+                          ("lookahead_buf", _f, (2, LA_SAMPLES)), ("la_write_idx", _u)])
+LEV_STATE_Q28 = np.dtype([("env_sq_l", _i), ("env_sq_r", _i), ("gain_smooth_db", _f),
+                          ("gain_q28", _i), ("gain_prev_q28", _i),
+                          ("lookahead_buf", _i, (2, LA_SAMPLES)), ("la_write_idx", _u)])
+
+# loudness.h:11-23 — LoudnessCoeffs (28 / 24 bytes)
+LOUD_F32 = np.dtype({
+    "names": ["sva1", "sva2", "sva3", "svm0", "svm1", "svm2", "bypass"],
+    "formats": [_f] * 6 + [_b], "offsets": [0, 4, 8, 12, 16, 20, 24], "itemsize": 28})
+LOUD_Q28 = np.dtype({
+    "names": ["b0", "b1", "b2", "a1", "a2", "bypass"],
+    "formats": [_i] * 5 + [_b], "offsets": [0, 4, 8, 12, 16, 20], "itemsize": 24})
+
+# pdm_generator.c:83-87 + loop locals :205-217 (our own packing, 9 words)
+PDM_STATE = np.dtype([("err1", _i), ("err2", _i), ("x1", _i), ("x2", _i), ("y1", _i), ("y2", _i),
+                      ("err_acc", _i), ("rng", _u), ("fade_in_pos", _u)])
+
+assert BIQUAD_F32.itemsize == 68 and BIQUAD_Q28.itemsize == 32 and EQ_PARAM.itemsize == 16
+assert CROSSPOINT.itemsize == 12 and OUTPUT.itemsize == 20
+assert XFEED_F32.itemsize == 28 and LEV_COEFFS.itemsize == 36
+assert LEV_STATE_F32.itemsize == 3864 and LEV_STATE_Q28.itemsize == 3864
+assert LOUD_F32.itemsize == 28 and LOUD_Q28.itemsize == 24 and PDM_STATE.itemsize == 36

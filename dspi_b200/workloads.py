@@ -1,0 +1,119 @@
+"""Synthetic workloads of BASELINE.json's configs.
+
+Parameter recipes (``EqParamPacket`` rows) and PCM inputs are generated from
+fixed seeds so tests, fixtures and the bench agree on the same bits.
+"""
+import numpy as np
+
+from . import layouts as L
+
+XORSHIFT_SEED = 123456789          # pdm_generator.c:62 — the reference's own PRNG seed
+
+
+def xorshift32(state):
+    """One xorshift32 step on a uint32 array (pdm_generator.c:63-68)."""
+    state = state ^ (state << np.uint32(13))
+    state = state ^ (state >> np.uint32(17))
+    state = state ^ (state << np.uint32(5))
+    return state
+
+
+def xorshift_s16(C, T, ch0=0):
+    """int16 [C, T]: per-channel xorshift32 stream seeded ``123456789 ^ ch``."""
+    st = (np.uint32(XORSHIFT_SEED) ^ (np.arange(C, dtype=np.uint32) + np.uint32(ch0))).astype(np.uint32)
+    st[st == 0] = 1
+    out = np.empty((C, T), np.int16)
+    with np.errstate(over="ignore"):
+        for t in range(T):
+            st = xorshift32(st)
+            out[:, t] = (st >> np.uint32(16)).astype(np.uint16).view(np.int16)
+    return out
+
+
+def inputs_f32(C, T, ch0=0):
+    """float32 [C, T] uniform in [-0.5, 0.5): s16 / 65536 (exact in float)."""
+    return (xorshift_s16(C, T, ch0).astype(np.float32) / np.float32(65536.0)).astype(np.float32)
+
+
+def inputs_q28(C, T, ch0=0):
+    """int32 [C, T]: s16 << 14 (usb_audio.c:1010), halved to keep ±0.5 full scale."""
+    return (xorshift_s16(C, T, ch0).astype(np.int32) << 13).astype(np.int32)
+
+
+ISO_OCTAVES = [31.5, 63.0, 125.0, 250.0, 500.0, 1000.0, 2000.0, 4000.0, 8000.0, 16000.0]
+
+
+def eq_params(variant, C, fs=96000.0, nbands=L.NUM_BANDS, seed=1, ch0=0):
+    """EQ_PARAM [C, MAX_BANDS] recipes.
+
+    ``A``      all-TDF2: 10 peaking bands at 13-42 kHz (>= fs/7.5, <= 0.45 fs)
+    ``B``      realistic: ISO octave centres; low shelf, 8 peaking, high shelf
+               (at 96 kHz: 9 SVF bands + 1 TDF2 band, dsp_pipeline.c:88)
+    ``mixed``  per-channel random types incl. LP/HP/flat (non-uniform structure)
+    Rows beyond ``nbands`` stay FLAT.  Per-channel streams are keyed by the
+    absolute channel index so shards of a larger job generate identical rows.
+    """
+    p = np.zeros((C, L.MAX_BANDS), L.EQ_PARAM)
+    p["freq"] = 1000.0
+    p["Q"] = 0.707
+    for c in range(C):
+        rng = np.random.default_rng([seed, ch0 + c])
+        u = rng.random((nbands, 4))
+        for b in range(nbands):
+            r = p[c, b]
+            r["channel"] = 0
+            r["band"] = b
+            gain = np.float32(-6.0 + 12.0 * u[b, 0])
+            if abs(gain) < 0.05:
+                gain = np.float32(0.5)
+            q = np.float32(0.7 + 3.3 * u[b, 1])
+            if variant == "A":
+                lo, hi = fs / 7.5 * 1.02, fs * 0.44
+                r["type"], r["freq"], r["Q"], r["gain_db"] = L.PEAKING, np.float32(lo + (hi - lo) * u[b, 2]), q, gain
+            elif variant == "B":
+                t = L.LOWSHELF if b == 0 else (L.HIGHSHELF if b == nbands - 1 else L.PEAKING)
+                qq = np.float32(0.707) if t != L.PEAKING else q
+                r["type"], r["freq"], r["Q"], r["gain_db"] = t, np.float32(ISO_OCTAVES[b % 10]), qq, gain
+            elif variant == "mixed":
+                t = int(u[b, 3] * 6) % 6
+                f = np.float32(20.0 * (fs * 0.45 / 20.0) ** u[b, 2])
+                r["type"], r["freq"], r["Q"], r["gain_db"] = t, f, q, gain
+            else:
+                raise ValueError(variant)
+    return p
+
+
+def eq_params_fast(variant, C, fs=96000.0, nbands=L.NUM_BANDS, seed=1, ch0=0):
+    """Vectorised generator for the big bench shapes (variants A and B only).
+
+    Not bit-compatible with :func:`eq_params` (different stream layout); used
+    where only the shape of the work matters, never for fixtures.
+    """
+    rng = np.random.default_rng([seed, ch0, C])
+    p = np.zeros((C, L.MAX_BANDS), L.EQ_PARAM)
+    p["freq"] = 1000.0
+    p["Q"] = 0.707
+    u = rng.random((C, nbands, 3)).astype(np.float32)
+    gain = (-6.0 + 12.0 * u[..., 0]).astype(np.float32)
+    gain[np.abs(gain) < 0.05] = 0.5
+    q = (0.7 + 3.3 * u[..., 1]).astype(np.float32)
+    p["band"][:, :nbands] = np.arange(nbands, dtype=np.uint8)[None, :]
+    p["gain_db"][:, :nbands] = gain
+    if variant == "A":
+        lo, hi = fs / 7.5 * 1.02, fs * 0.44
+        p["type"][:, :nbands] = L.PEAKING
+        p["freq"][:, :nbands] = (lo + (hi - lo) * u[..., 2]).astype(np.float32)
+        p["Q"][:, :nbands] = q
+    elif variant == "B":
+        types = np.full(nbands, L.PEAKING, np.uint8)
+        types[0] = L.LOWSHELF
+        types[nbands - 1] = L.HIGHSHELF
+        p["type"][:, :nbands] = types[None, :]
+        p["freq"][:, :nbands] = np.array([ISO_OCTAVES[b % 10] for b in range(nbands)], np.float32)[None, :]
+        qq = q.copy()
+        qq[:, 0] = 0.707
+        qq[:, nbands - 1] = 0.707
+        p["Q"][:, :nbands] = qq
+    else:
+        raise ValueError(variant)
+    return p
