@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the DSPi hot path on B200 (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One *step* = one pass of the 10-band EQ cascade over one batch: 65 536 channels x 6144 samples
+(= 64 firmware packets of 96 frames @96 kHz) per GPU, channel-major float32, in place.
+N>1 is launched by torchrun, one rank per GPU; channels shard with no data-path collective
+(weak scaling: 65 536 channels per GPU, 524 288 at N=8 = BASELINE config 5).
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio samples/sec (whole box) at 65536ch x 10-band EQ, 96 kHz; % HBM roofline"
+CHANNELS_PER_GPU = 65536
+FS = 96000.0
+ALG_BYTES_PER_SAMPLE = 8          # 4 B read + 4 B written per channel-sample
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+                 0x100: "display_clock_setting"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "n_samples": len(self.samples)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(variant, arith, frames, target_seconds, steps=1, warmup=0):
+    """Times the reference's own dsp_process_channel_block (oracle/_ref, compiled from the unmodified
+    sources) - or the oracle port when _ref is absent - on all host threads over a bounded sample of
+    the same workload.  Returns (samples_per_s, info)."""
+    from dspi_b200 import layouts as L, workloads as W
+    from tests.orc import Oracle, Ref
+    threads = host_threads()
+    q = arith == "q28"
+    use_ref = Ref.available()
+    if use_ref:
+        ref = Ref(arith)
+        kind = "reference"
+    else:
+        ref = None
+        kind = "port"
+    orc = Oracle()
+    # probe: 64 channels per thread, one packet row
+    def make(Cn):
+        params = W.eq_params_fast(variant if not q else "B", Cn, fs=FS, seed=1)
+        bq = np.zeros(params.shape, L.BIQUAD_Q28 if q else L.BIQUAD_F32)
+        orc.eq_coeffs(q, params, bq, FS)
+        rng = np.random.default_rng(0)
+        if q:
+            x = rng.integers(-2**27, 2**27, (Cn, frames), dtype=np.int64).astype(np.int32)
+        else:
+            x = (rng.random((Cn, frames), dtype=np.float32) - np.float32(0.5))
+        return bq, x
+
+    def run(bq, x):
+        if use_ref:
+            return ref.eq_many_mt(bq, x, 10, 96, threads)
+        return orc.eq_many_mt(arith, bq, x, 10, 96, threads)
+
+    Cp = 16 * threads
+    bq, x = make(Cp)
+    dt = run(bq, x)
+    rate = Cp * frames / dt
+    Cn = int(max(threads, min(CHANNELS_PER_GPU, rate * target_seconds / frames)))
+    Cn = max(threads, (Cn // threads) * threads)
+    bq, x = make(Cn)
+    for _ in range(warmup):
+        run(bq.copy(), x.copy())
+    times = []
+    for _ in range(steps):
+        times.append(run(bq, x))
+    sps = Cn * frames * len(times) / sum(times)
+    info = {"value": sps, "unit": "samples/s", "cores": threads, "kind": kind,
+            "sample": f"{Cn} of {CHANNELS_PER_GPU} channels x {frames} samples, 96-sample packets, {len(times)} pass(es), "
+                      f"{'oracle/_ref (reference sources, ' + ('-mfma -ffp-contract=fast' if arith == 'f32f' else '-ffp-contract=off' if arith == 'f32s' else '-fwrapv') + ')' if use_ref else 'oracle port'}",
+            "seconds": sum(times)}
+    return sps, info, Cn
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dspi_b200", choices=["dspi_b200", "reference"])
+    ap.add_argument("--variant", default="A", choices=["A", "B"])
+    ap.add_argument("--arith", default="f32f", choices=["f32f", "f32s", "q28"])
+    ap.add_argument("--frames", type=int, default=6144)
+    ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = (f"BASELINE configs[1]: {args.channels} channels x 10-band cascade @96 kHz, {args.arith}, variant "
+                f"{args.variant} ({'all-TDF2 biquads' if args.variant == 'A' else '9 SVF + 1 TDF2'}), {args.frames} samples/step")
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sps, info, Cn = cpu_reference_run(args.variant, args.arith, args.frames, target_seconds=4.0, steps=args.steps, warmup=args.warmup)
+        line = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * info["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"f32f": "f32", "f32s": "f32", "q28": "int32"}[args.arith], "data": "synthetic", "impl": "reference",
+                "config": {"workload": workload, "sample_channels": Cn, "parallelism": f"{info['cores']} host threads"},
+                "cpu_baseline": {k: info[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from dspi_b200 import api, layouts as L, workloads as W
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    q = args.arith == "q28"
+    Cn, T = args.channels, args.frames
+    ch0 = rank * Cn                                       # contiguous channel shard of the whole job
+
+    params = W.eq_params_fast(args.variant if not q else "B", Cn, fs=FS, seed=1, ch0=ch0)
+    bq = api.compute_coefficients(params, q28=q, fs=FS)
+    eng = api.EqEngine(args.arith, Cn, device=local_rank)
+    eng.upload(bq)
+
+    # rotating input buffers, each larger than L2 (126 MB): 65536 x 6144 x 4 B = 1.5 GiB
+    nbuf = max(2, min(8, args.steps))
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    bufs = []
+    for _ in range(nbuf):
+        if q:
+            b = torch.randint(-2**27, 2**27, (Cn, T), dtype=torch.int32, device="cuda", generator=gen)
+        else:
+            b = torch.rand((Cn, T), dtype=torch.float32, device="cuda", generator=gen) - 0.5
+        bufs.append(b)
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+
+    def step(i):
+        eng.process_device(bufs[i % nbuf].data_ptr(), T, T)
+
+    for i in range(args.warmup):
+        step(i)
+    eng.sync()
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    ev1.record(stream)
+    eng.sync()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    total_samples = float(Cn) * T * args.steps * world
+    value = total_samples / (ms * 1e-3)
+
+    # per-kernel roofline: the step IS one launch of the cascade kernel
+    peak, peak_src = measured_peak_gbs()
+    per_gpu_sps = float(Cn) * T * args.steps / (ms * 1e-3)
+    achieved = per_gpu_sps * ALG_BYTES_PER_SAMPLE / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "eq_q28_kernel" if q else "eq_f32_kernel",
+                "algorithmic_bytes_per_launch": Cn * T * ALG_BYTES_PER_SAMPLE,
+                "note": "FP32-issue bound, not HBM bound: see DESIGN.md (60 FMA-pipe lane-ops per sample)"}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(f"{roofline['kernel']}:{args.arith}:{args.variant}")
+        except Exception:
+            pass
+
+    # end to end through the C ABI with HOST buffers (pinned): H2D + kernel(s) + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        pin = api.PinnedBuffer((Cn, T), np.int32 if q else np.float32)
+        src = bufs[0].cpu().numpy()
+        pin.array[...] = src
+        n_e2e = max(2, min(5, args.steps))
+        eng.process_host(pin.array)                       # warm-up (allocates staging)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            eng.process_host(pin.array)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": float(Cn) * T * n_e2e * world / dt, "unit": "samples/s", "h2d_bytes_per_step": Cn * T * 4,
+               "d2h_bytes_per_step": Cn * T * 4, "steps": n_e2e,
+               "path": "dspi_eq_process_host: pinned host [C][T] -> chunked cudaMemcpy2DAsync H2D / kernel / D2H on 3 streams"}
+        pin.free()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        _, cpu, _ = cpu_reference_run(args.variant, args.arith, T, target_seconds=10.0)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"f32f": "f32", "f32s": "f32", "q28": "int32"}[args.arith], "data": "synthetic",
+                "config": {"workload": workload, "channels_per_gpu": Cn, "frames_per_step": T, "sample_rate_hz": FS,
+                           "arith": args.arith, "variant": args.variant, "parallelism": f"channel-sharded dp{world}, no collective on the data path",
+                           "l2": f"inputs larger than L2: {nbuf} rotating buffers of {Cn * T * 4 / 2**30:.2f} GiB", "layout": "channel-major [C][T], in place"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "realtime_factor": value / (Cn * world * FS)}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

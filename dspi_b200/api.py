@@ -1,0 +1,172 @@
+"""ctypes binding of the C ABI (``include/dspi_b200.h``) — the call a Python host makes.
+
+There is no CPU path in this package: if ``libdspi_b200.so`` is missing or no
+sm_100 device is visible, construction fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import layouts as L
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdspi_b200.so")
+
+ARITH_F32_FUSED, ARITH_F32_STRICT, ARITH_Q28 = 0, 1, 2
+ARITH = {"f32f": ARITH_F32_FUSED, "f32s": ARITH_F32_STRICT, "q28": ARITH_Q28}
+
+# every symbol include/dspi_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "dspi_last_error", "dspi_device_count", "dspi_compute_coefficients_f32", "dspi_compute_coefficients_q28",
+    "dspi_eq_create", "dspi_eq_destroy", "dspi_eq_upload_biquads", "dspi_eq_download_biquads", "dspi_eq_set_param",
+    "dspi_eq_process_device", "dspi_eq_process_host", "dspi_eq_sync", "dspi_eq_stream", "dspi_eq_launch_count",
+    "dspi_host_alloc", "dspi_host_free",
+]
+
+
+class DspiError(RuntimeError):
+    pass
+
+
+class _EqDesc(C.Structure):
+    _fields_ = [("arith", C.c_uint32), ("n_channels", C.c_uint32), ("n_bands", C.c_uint32),
+                ("device", C.c_int32), ("flags", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (never built implicitly here: see ``dspi_b200.build``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DspiError(f"{LIB_PATH} is missing - build it with `python -m dspi_b200.build` "
+                            "(there is no CPU fallback)")
+        h = C.CDLL(LIB_PATH)
+        vp, u32 = C.c_void_p, C.c_uint32
+        h.dspi_last_error.restype = C.c_char_p
+        h.dspi_device_count.restype = C.c_int
+        h.dspi_compute_coefficients_f32.argtypes = [vp, vp, C.c_float]
+        h.dspi_compute_coefficients_q28.argtypes = [vp, vp, C.c_float]
+        h.dspi_eq_create.argtypes = [C.POINTER(vp), C.POINTER(_EqDesc)]
+        h.dspi_eq_destroy.argtypes = [vp]
+        h.dspi_eq_upload_biquads.argtypes = [vp, u32, u32, vp]
+        h.dspi_eq_download_biquads.argtypes = [vp, u32, u32, vp]
+        h.dspi_eq_set_param.argtypes = [vp, u32, vp, C.c_float]
+        h.dspi_eq_process_device.argtypes = [vp, vp, u32, u32]
+        h.dspi_eq_process_host.argtypes = [vp, vp, u32]
+        h.dspi_eq_sync.argtypes = [vp]
+        h.dspi_eq_stream.argtypes = [vp]
+        h.dspi_eq_stream.restype = vp
+        h.dspi_eq_launch_count.argtypes = [vp]
+        h.dspi_eq_launch_count.restype = C.c_uint64
+        h.dspi_host_alloc.argtypes = [C.c_size_t]
+        h.dspi_host_alloc.restype = vp
+        h.dspi_host_free.argtypes = [vp]
+        _lib = h
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise DspiError(f"dspi error {rc}: {lib().dspi_last_error().decode()}")
+
+
+def compute_coefficients(params, q28=False, fs=48000.0, biquads=None):
+    """Host-side ``dsp_compute_coefficients`` over an array of recipes.
+
+    ``params``: EQ_PARAM array (clamped in place like the reference);
+    ``biquads``: matching BIQUAD_* array to update (state kept) or None for fresh zeros.
+    """
+    h = lib()
+    dt = L.BIQUAD_Q28 if q28 else L.BIQUAD_F32
+    if biquads is None:
+        biquads = np.zeros(params.shape, dt)
+    fn = h.dspi_compute_coefficients_q28 if q28 else h.dspi_compute_coefficients_f32
+    pp, bb = params.reshape(-1), biquads.reshape(-1)
+    bp, bbp = pp.ctypes.data, bb.ctypes.data
+    for i in range(pp.shape[0]):
+        fn(bp + i * pp.dtype.itemsize, bbp + i * bb.dtype.itemsize, fs)
+    return biquads
+
+
+class PinnedBuffer:
+    """Page-locked host memory viewed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = lib().dspi_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise DspiError("dspi_host_alloc failed")
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().dspi_host_free(self.ptr)
+            self.ptr = None
+
+
+class EqEngine:
+    """Many independent 10-band cascades on one B200 (``dspi_eq_*``)."""
+
+    def __init__(self, arith, n_channels, n_bands=L.NUM_BANDS, device=0):
+        self.arith = ARITH[arith] if isinstance(arith, str) else int(arith)
+        self.q28 = self.arith == ARITH_Q28
+        self.n_channels, self.n_bands, self.device = int(n_channels), int(n_bands), int(device)
+        self.biquad_dtype = L.BIQUAD_Q28 if self.q28 else L.BIQUAD_F32
+        self.sample_dtype = np.int32 if self.q28 else np.float32
+        self._h = C.c_void_p()
+        desc = _EqDesc(self.arith, self.n_channels, self.n_bands, self.device, 0)
+        _check(lib().dspi_eq_create(C.byref(self._h), C.byref(desc)))
+
+    def close(self):
+        if self._h:
+            lib().dspi_eq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, biquads, ch0=0):
+        b = np.ascontiguousarray(biquads)
+        assert b.dtype == self.biquad_dtype and b.ndim == 2 and b.shape[1] == L.MAX_BANDS
+        _check(lib().dspi_eq_upload_biquads(self._h, ch0, b.shape[0], b.ctypes.data))
+
+    def download(self, n=None, ch0=0):
+        n = self.n_channels - ch0 if n is None else n
+        out = np.zeros((n, L.MAX_BANDS), self.biquad_dtype)
+        _check(lib().dspi_eq_download_biquads(self._h, ch0, n, out.ctypes.data))
+        return out
+
+    def set_param(self, channel, param, fs):
+        p = np.array([param], dtype=L.EQ_PARAM) if not isinstance(param, np.ndarray) else param.reshape(1).copy()
+        _check(lib().dspi_eq_set_param(self._h, channel, p.ctypes.data, fs))
+        return p[0]
+
+    def process_device(self, dev_ptr, T, ld=None):
+        _check(lib().dspi_eq_process_device(self._h, C.c_void_p(int(dev_ptr)), T, T if ld is None else ld))
+
+    def process_host(self, samples):
+        """``samples``: C-contiguous [n_channels, T] numpy array (or PinnedBuffer.array); in place."""
+        assert samples.flags["C_CONTIGUOUS"] and samples.dtype == self.sample_dtype and samples.shape[0] == self.n_channels
+        _check(lib().dspi_eq_process_host(self._h, samples.ctypes.data, samples.shape[1]))
+
+    def sync(self):
+        _check(lib().dspi_eq_sync(self._h))
+
+    @property
+    def stream(self):
+        return lib().dspi_eq_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().dspi_eq_launch_count(self._h))

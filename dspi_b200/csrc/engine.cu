@@ -1,0 +1,348 @@
+// engine.cu — the C-ABI of include/dspi_b200.h: EQ engine (K1 float / K2 Q28).
+//
+// No CPU fallback lives here: without an sm_100 device every create call fails with
+// DSPI_ENODEV and nothing else can be reached.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "eq_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_OK(expr)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t err__ = (expr);                                                                         \
+        if (err__ != cudaSuccess) return fail(DSPI_ECUDA, "%s -> %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+constexpr int kHostBufs = 3;
+
+}  // namespace
+
+struct dspi_eq {
+    dspi_eq_desc desc;
+    int cpl;                 // channels per lane (float: 1 or 2; Q28: 1)
+    uint32_t rows;           // channels per group = 32 * cpl
+    uint32_t n_groups;
+    uint32_t c_pad;          // n_groups * rows
+    cudaStream_t stream, s_h2d, s_d2h;
+    void *d_aos;             // Biquad[c_pad][12] in the reference layout (device mirror)
+    void *d_coef;            // packed coefficient + state store
+    uint64_t *d_modes;       // float only
+    size_t aos_elem;
+    uint64_t launches;
+    // host-path staging
+    void *d_stage[kHostBufs];
+    size_t stage_bytes;
+    cudaEvent_t ev_in[kHostBufs], ev_done[kHostBufs], ev_out[kHostBufs];
+    // tensor-map cache
+    CUtensorMap tmap;
+    void *tm_ptr;
+    uint32_t tm_T, tm_ld, tm_rows;
+};
+
+extern "C" {
+
+const char *dspi_last_error(void) { return g_err; }
+
+int dspi_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+void *dspi_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void dspi_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int dspi_eq_create(dspi_eq **out, const dspi_eq_desc *desc)
+{
+    if (!out || !desc) return fail(DSPI_EINVAL, "null argument");
+    *out = nullptr;
+    if (desc->arith > DSPI_ARITH_Q28) return fail(DSPI_EINVAL, "unknown arith %u", desc->arith);
+    if (desc->n_channels == 0) return fail(DSPI_EINVAL, "n_channels must be > 0");
+    if (desc->n_bands == 0 || desc->n_bands > DSPI_MAX_BANDS) return fail(DSPI_EINVAL, "n_bands must be 1..%d", DSPI_MAX_BANDS);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(DSPI_ENODEV, "no CUDA device (there is no CPU fallback)"); }
+    if (desc->device < 0 || desc->device >= ndev) return fail(DSPI_ENODEV, "device %d out of range (%d visible)", desc->device, ndev);
+    int major = 0;
+    CU_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, desc->device));
+    if (major != 10) return fail(DSPI_ENODEV, "device %d has compute capability %d.x; the kernels are built for sm_100a only", desc->device, major);
+    if (!encode_fn()) return fail(DSPI_ENODEV, "driver does not export cuTensorMapEncodeTiled");
+    CU_OK(cudaSetDevice(desc->device));
+
+    dspi_eq *e = new (std::nothrow) dspi_eq();
+    if (!e) return fail(DSPI_ENOMEM, "host allocation failed");
+    memset(e, 0, sizeof(*e));
+    e->desc = *desc;
+    const bool q28 = desc->arith == DSPI_ARITH_Q28;
+    e->cpl = 2;
+    if (const char *v = getenv("DSPI_F32_CPL")) e->cpl = atoi(v) == 1 ? 1 : 2;   // 1 = scalar FFMA variant, for A/B measurement
+    if (q28) e->cpl = 1;
+    e->rows = 32u * e->cpl;
+    e->n_groups = (desc->n_channels + e->rows - 1) / e->rows;
+    e->c_pad = e->n_groups * e->rows;
+    e->aos_elem = q28 ? sizeof(dspi_biquad_q28) : sizeof(dspi_biquad_f32);
+
+    cudaError_t err;
+    const size_t aos_bytes = (size_t)e->c_pad * DSPI_MAX_BANDS * e->aos_elem;
+    const size_t coef_bytes = q28 ? (size_t)e->n_groups * DSPI_MAX_BANDS * 20 * 32 * 4 : (size_t)e->c_pad * DSPI_MAX_BANDS * 8 * 4;
+    if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) goto cuda_fail;
+    if ((err = cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) goto cuda_fail;
+    if ((err = cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) goto cuda_fail;
+    for (int i = 0; i < kHostBufs; i++) {
+        if ((err = cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) goto cuda_fail;
+        if ((err = cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) goto cuda_fail;
+        if ((err = cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) goto cuda_fail;
+    }
+    if ((err = cudaMalloc(&e->d_aos, aos_bytes)) != cudaSuccess) goto cuda_fail;
+    if ((err = cudaMalloc(&e->d_coef, coef_bytes)) != cudaSuccess) goto cuda_fail;
+    if ((err = cudaMemsetAsync(e->d_aos, 0, aos_bytes, e->stream)) != cudaSuccess) goto cuda_fail;
+    if ((err = cudaMemsetAsync(e->d_coef, 0, coef_bytes, e->stream)) != cudaSuccess) goto cuda_fail;
+    if (!q28) {
+        if ((err = cudaMalloc(&e->d_modes, (size_t)e->c_pad * 8)) != cudaSuccess) goto cuda_fail;
+        if ((err = cudaMemsetAsync(e->d_modes, 0, (size_t)e->c_pad * 8, e->stream)) != cudaSuccess) goto cuda_fail;
+    }
+    // every band of every (padding) channel starts bypassed, like dsp_init_default_filters() (dsp_pipeline.c:177-199)
+    if ((err = cudaStreamSynchronize(e->stream)) != cudaSuccess) goto cuda_fail;
+    *out = e;
+    return DSPI_OK;
+
+cuda_fail:
+    fail(DSPI_ECUDA, "engine setup: %s", cudaGetErrorString(err));
+    dspi_eq_destroy(e);
+    return err == cudaErrorMemoryAllocation ? DSPI_ENOMEM : DSPI_ECUDA;
+}
+
+int dspi_eq_destroy(dspi_eq *e)
+{
+    if (!e) return DSPI_OK;
+    cudaSetDevice(e->desc.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->s_h2d) cudaStreamSynchronize(e->s_h2d);
+    if (e->s_d2h) cudaStreamSynchronize(e->s_d2h);
+    for (int i = 0; i < kHostBufs; i++) {
+        if (e->d_stage[i]) cudaFree(e->d_stage[i]);
+        if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
+        if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+        if (e->ev_out[i]) cudaEventDestroy(e->ev_out[i]);
+    }
+    if (e->d_aos) cudaFree(e->d_aos);
+    if (e->d_coef) cudaFree(e->d_coef);
+    if (e->d_modes) cudaFree(e->d_modes);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
+    if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+    delete e;
+    cudaGetLastError();
+    return DSPI_OK;
+}
+
+static int check_range(dspi_eq *e, uint32_t ch0, uint32_t n, const void *p)
+{
+    if (!e || !p) return fail(DSPI_EINVAL, "null argument");
+    if ((uint64_t)ch0 + n > e->desc.n_channels) return fail(DSPI_ERANGE, "channels [%u, %u) outside engine of %u", ch0, ch0 + n, e->desc.n_channels);
+    return DSPI_OK;
+}
+
+int dspi_eq_upload_biquads(dspi_eq *e, uint32_t ch0, uint32_t n, const void *biquads)
+{
+    int rc = check_range(e, ch0, n, biquads);
+    if (rc) return rc;
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(e->desc.device));
+    const size_t row = (size_t)DSPI_MAX_BANDS * e->aos_elem;
+    CU_OK(cudaMemcpyAsync((char *)e->d_aos + ch0 * row, biquads, n * row, cudaMemcpyHostToDevice, e->stream));
+    if (e->desc.arith == DSPI_ARITH_Q28)
+        CU_OK(dspi::launch_pack_q28((const dspi_biquad_q28 *)e->d_aos, ch0, n, (int32_t *)e->d_coef, e->stream));
+    else
+        CU_OK(dspi::launch_pack_f32((const dspi_biquad_f32 *)e->d_aos, ch0, n, (float *)e->d_coef, e->d_modes, e->cpl, e->stream));
+    e->launches++;
+    CU_OK(cudaStreamSynchronize(e->stream));     // the caller may reuse `biquads` immediately
+    return DSPI_OK;
+}
+
+int dspi_eq_download_biquads(dspi_eq *e, uint32_t ch0, uint32_t n, void *biquads)
+{
+    int rc = check_range(e, ch0, n, biquads);
+    if (rc) return rc;
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(e->desc.device));
+    if (e->desc.arith == DSPI_ARITH_Q28)
+        CU_OK(dspi::launch_unpack_q28((dspi_biquad_q28 *)e->d_aos, ch0, n, (const int32_t *)e->d_coef, e->stream));
+    else
+        CU_OK(dspi::launch_unpack_f32((dspi_biquad_f32 *)e->d_aos, ch0, n, (const float *)e->d_coef, e->cpl, e->stream));
+    e->launches++;
+    const size_t row = (size_t)DSPI_MAX_BANDS * e->aos_elem;
+    CU_OK(cudaMemcpyAsync(biquads, (char *)e->d_aos + ch0 * row, n * row, cudaMemcpyDeviceToHost, e->stream));
+    CU_OK(cudaStreamSynchronize(e->stream));
+    return DSPI_OK;
+}
+
+int dspi_eq_set_param(dspi_eq *e, uint32_t channel, dspi_eq_param *p, float sample_rate)
+{
+    if (!e || !p) return fail(DSPI_EINVAL, "null argument");
+    if (channel >= e->desc.n_channels) return fail(DSPI_ERANGE, "channel %u outside engine of %u", channel, e->desc.n_channels);
+    if (p->band >= DSPI_MAX_BANDS) return fail(DSPI_ERANGE, "band %u >= %d", p->band, DSPI_MAX_BANDS);
+    // main.c:826-857: between packets, recompute filters[ch][band] in place (state kept unless the topology flips)
+    alignas(8) unsigned char rowbuf[DSPI_MAX_BANDS * sizeof(dspi_biquad_f32)];
+    int rc = dspi_eq_download_biquads(e, channel, 1, rowbuf);
+    if (rc) return rc;
+    if (e->desc.arith == DSPI_ARITH_Q28)
+        dspi_compute_coefficients_q28(p, &((dspi_biquad_q28 *)rowbuf)[p->band], sample_rate);
+    else
+        dspi_compute_coefficients_f32(p, &((dspi_biquad_f32 *)rowbuf)[p->band], sample_rate);
+    return dspi_eq_upload_biquads(e, channel, 1, rowbuf);
+}
+
+static int make_tmap(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint32_t n_rows, CUtensorMap *out)
+{
+    const cuuint64_t gdim[2] = { T, n_rows };
+    const cuuint64_t gstride[1] = { (cuuint64_t)ld * 4 };
+    const cuuint32_t box[2] = { 32, e->rows };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUtensorMapDataType dt = e->desc.arith == DSPI_ARITH_Q28 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r = encode_fn()(out, dt, 2, d_samples, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DSPI_ECUDA, "cuTensorMapEncodeTiled failed (%d) for T=%u ld=%u rows=%u", (int)r, T, ld, n_rows);
+    return DSPI_OK;
+}
+
+// launch over all channels of the engine on `stream`
+static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStream_t stream)
+{
+    dspi::EqLaunch a;
+    memset(&a, 0, sizeof(a));
+    const bool tma_ok = (ld % 4 == 0) && (((uintptr_t)d_samples & 15) == 0);
+    if (tma_ok) {
+        if (e->tm_ptr != d_samples || e->tm_T != T || e->tm_ld != ld || e->tm_rows != e->desc.n_channels) {
+            int rc = make_tmap(e, d_samples, T, ld, e->desc.n_channels, &e->tmap);
+            if (rc) return rc;
+            e->tm_ptr = d_samples; e->tm_T = T; e->tm_ld = ld; e->tm_rows = e->desc.n_channels;
+        }
+        a.tmap = e->tmap;
+    }
+    a.samples = d_samples;
+    a.ld = ld;
+    a.coef = e->d_coef;
+    a.modes = e->d_modes;
+    a.n_groups = e->n_groups;
+    a.n_rows = e->desc.n_channels;
+    a.T = T;
+    a.n_bands = e->desc.n_bands;
+    a.use_tma = tma_ok ? 1u : 0u;
+    cudaError_t err;
+    if (e->desc.arith == DSPI_ARITH_Q28) err = dspi::launch_eq_q28(a, stream);
+    else err = dspi::launch_eq_f32(a, e->desc.arith == DSPI_ARITH_F32_FUSED, e->cpl, stream);
+    if (err != cudaSuccess) return fail(DSPI_ECUDA, "EQ kernel launch: %s", cudaGetErrorString(err));
+    e->launches++;
+    return DSPI_OK;
+}
+
+int dspi_eq_process_device(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld)
+{
+    if (!e || !d_samples) return fail(DSPI_EINVAL, "null argument");
+    if (T == 0) return DSPI_OK;
+    if (ld < T) return fail(DSPI_EINVAL, "row stride %u < T %u", ld, T);
+    CU_OK(cudaSetDevice(e->desc.device));
+    return launch_eq(e, d_samples, T, ld, e->stream);
+}
+
+int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T)
+{
+    if (!e || !h_samples) return fail(DSPI_EINVAL, "null argument");
+    if (T == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(e->desc.device));
+    const uint32_t C = e->desc.n_channels;
+    // time-chunked pipeline: all channels x Tc samples per step, so every launch fills the GPU and the
+    // filter state is carried from chunk to chunk exactly as from packet to packet in the firmware.
+    uint32_t Tc = (uint32_t)(((size_t)96 << 20) / ((size_t)C * 4));
+    Tc = (Tc / 32) * 32;
+    if (Tc < 32) Tc = 32;
+    if (Tc >= T) Tc = (T + 3) & ~3u;
+    const size_t need = (size_t)C * Tc * 4;
+    if (need > e->stage_bytes) {
+        for (int i = 0; i < kHostBufs; i++) {
+            if (e->d_stage[i]) { cudaFree(e->d_stage[i]); e->d_stage[i] = nullptr; }
+        }
+        e->stage_bytes = 0;
+        for (int i = 0; i < kHostBufs; i++) {
+            if (cudaMalloc(&e->d_stage[i], need) != cudaSuccess) { cudaGetLastError(); return fail(DSPI_ENOMEM, "staging buffer of %zu bytes", need); }
+        }
+        e->stage_bytes = need;
+    }
+    const uint32_t nchunks = (T + Tc - 1) / Tc;
+    char *host = (char *)h_samples;
+    for (uint32_t k = 0; k < nchunks; k++) {
+        const int b = k % kHostBufs;
+        const uint32_t t0 = k * Tc, n = (T - t0 < Tc) ? (T - t0) : Tc;
+        if (k >= (uint32_t)kHostBufs) CU_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_out[b], 0));       // buffer drained
+        CU_OK(cudaMemcpy2DAsync(e->d_stage[b], (size_t)Tc * 4, host + (size_t)t0 * 4, (size_t)T * 4, (size_t)n * 4, C,
+                                cudaMemcpyHostToDevice, e->s_h2d));
+        CU_OK(cudaEventRecord(e->ev_in[b], e->s_h2d));
+        CU_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
+        e->tm_ptr = nullptr;                                                                      // chunk geometry changes at the tail
+        int rc = launch_eq(e, e->d_stage[b], n, Tc, e->stream);
+        if (rc) return rc;
+        CU_OK(cudaEventRecord(e->ev_done[b], e->stream));
+        CU_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[b], 0));
+        CU_OK(cudaMemcpy2DAsync(host + (size_t)t0 * 4, (size_t)T * 4, e->d_stage[b], (size_t)Tc * 4, (size_t)n * 4, C,
+                                cudaMemcpyDeviceToHost, e->s_d2h));
+        CU_OK(cudaEventRecord(e->ev_out[b], e->s_d2h));
+    }
+    CU_OK(cudaStreamSynchronize(e->s_d2h));
+    return DSPI_OK;
+}
+
+int dspi_eq_sync(dspi_eq *e)
+{
+    if (!e) return fail(DSPI_EINVAL, "null argument");
+    CU_OK(cudaSetDevice(e->desc.device));
+    CU_OK(cudaStreamSynchronize(e->stream));
+    return DSPI_OK;
+}
+
+void *dspi_eq_stream(dspi_eq *e) { return e ? (void *)e->stream : nullptr; }
+uint64_t dspi_eq_launch_count(dspi_eq *e) { return e ? e->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// eq_kernels.cuh — declarations shared by the EQ kernels and the engine (C-ABI) code.
+#pragma once
+#include "dspi_common.cuh"
+#include "dspi_b200.h"
+
+namespace dspi {
+
+constexpr int kMaxBands = DSPI_MAX_BANDS;
+
+// per-band topology of one channel, 4 bits per band in a 64-bit word (band b -> bits 4b..4b+3)
+enum : uint32_t {
+    kModeBypass = 0,   // Biquad.bypass                       (dsp_pipeline.c:288)
+    kModeTdf2   = 1,   // !use_svf                            (dsp_pipeline.c:347-362)
+    kModeSvfLP  = 2,   // use_svf, svf_type == FILTER_LOWPASS (dsp_pipeline.c:299-309)
+    kModeSvfHP  = 3,   //                    FILTER_HIGHPASS  (:310-320)
+    kModeSvfPK  = 4,   //                    FILTER_PEAKING   (:321-331)
+    kModeSvfSH  = 5    // default: shelves, general mix       (:332-342)
+};
+
+struct EqLaunch {
+    CUtensorMap tmap;      // [C rows][T] tiled map, box {32, rows-per-warp}, SWIZZLE_128B
+    void *samples;         // device base (fallback path)
+    uint32_t ld;           // row stride in elements
+    void *coef;            // packed coefficient/state store
+    const uint64_t *modes; // f32 only
+    uint32_t n_groups;     // groups of (32 * channels-per-lane) channels
+    uint32_t n_rows;       // valid channel rows in `samples`
+    uint32_t T;
+    uint32_t n_bands;
+    uint32_t use_tma;
+};
+
+// K1 — float cascade.  cpl: channels per lane (1 scalar FFMA, 2 packed FFMA2)
+cudaError_t launch_eq_f32(const EqLaunch &a, bool fused, int cpl, cudaStream_t stream);
+cudaError_t launch_pack_f32(const dspi_biquad_f32 *aos, uint32_t ch0, uint32_t n, float *coef, uint64_t *modes, int cpl, cudaStream_t stream);
+cudaError_t launch_unpack_f32(dspi_biquad_f32 *aos, uint32_t ch0, uint32_t n, const float *coef, int cpl, cudaStream_t stream);
+
+// K2 — Q28 cascade (1 channel per lane)
+cudaError_t launch_eq_q28(const EqLaunch &a, cudaStream_t stream);
+cudaError_t launch_pack_q28(const dspi_biquad_q28 *aos, uint32_t ch0, uint32_t n, int32_t *coef, cudaStream_t stream);
+cudaError_t launch_unpack_q28(dspi_biquad_q28 *aos, uint32_t ch0, uint32_t n, const int32_t *coef, cudaStream_t stream);
+
+}  // namespace dspi

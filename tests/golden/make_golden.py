@@ -1,0 +1,103 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference sources compiled on the host
+(oracle/_ref/*.so, built by `make -C oracle ref` from /root/reference).  Run in the build
+container only (the GPU box has no /root/reference); the outputs are committed.
+
+    python tests/golden/make_golden.py
+
+Fixture A  "cfg1": BASELINE config 1 - 2 channels x 3 bands @48 kHz:
+           low shelf 100 Hz +4 dB Q.707 (SVF), peaking 1 kHz -3 dB Q1.4 (SVF), high shelf
+           10 kHz +2 dB Q.707 (TDF2), bands 3-9 flat; inputs: impulse, 1 kHz sine -6 dBFS,
+           log sweep 20 Hz-20 kHz, xorshift32 s16 noise; 100 packets x 48 samples.
+Fixture B  "mix":  24 channels, random per-band types (all six), 96 kHz, 960 samples.
+Each holds coefficients (reference dsp_compute_coefficients), inputs, and outputs + final
+filter state of dsp_process_channel_block for the strict, fused and Q28 builds.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from dspi_b200 import layouts as L          # noqa: E402
+from dspi_b200 import workloads as W        # noqa: E402
+from tests.orc import Ref, build_oracle     # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def cfg1_params():
+    p = np.zeros((2, L.MAX_BANDS), L.EQ_PARAM)
+    p["freq"], p["Q"] = 1000.0, 0.707
+    for c in range(2):
+        p[c, 0] = (c, 0, L.LOWSHELF, 0, 100.0, 0.707, 4.0)
+        p[c, 1] = (c, 1, L.PEAKING, 0, 1000.0, 1.4, -3.0)
+        p[c, 2] = (c, 2, L.HIGHSHELF, 0, 10000.0, 0.707, 2.0)
+    return p
+
+
+def cfg1_inputs(T):
+    t = np.arange(T, dtype=np.float64)
+    fs = 48000.0
+    imp = np.zeros(T, np.float32); imp[0] = 1.0
+    sine = (0.5 * np.sin(2 * np.pi * 1000.0 * t / fs)).astype(np.float32)
+    k = np.log(20000.0 / 20.0) / (T / fs)
+    sweep = (0.5 * np.sin(2 * np.pi * 20.0 * (np.exp(k * t / fs) - 1.0) / k)).astype(np.float32)
+    noise = W.inputs_f32(1, T)[0]
+    return {"impulse": imp, "sine": sine, "sweep": sweep, "noise": noise}
+
+
+def run(refs, params, x_f32, fs, packet):
+    out = {}
+    for fl in ("f32s", "f32f"):
+        bq = np.zeros(params.shape, L.BIQUAD_F32)
+        refs["f32s"].eq_coeffs(params.copy(), bq, fs)       # coefficients are data: always the strict build's
+        y = x_f32.copy()
+        b = bq.copy()
+        refs[fl].eq_many(b, y, 10, packet)
+        out[fl] = (bq, y, b)
+    bq = np.zeros(params.shape, L.BIQUAD_Q28)
+    refs["q28"].eq_coeffs(params.copy(), bq, fs)
+    xq = np.round(x_f32.astype(np.float64) * (1 << 28)).astype(np.int64).clip(-2**31, 2**31 - 1).astype(np.int32)
+    y = xq.copy()
+    b = bq.copy()
+    refs["q28"].eq_many(b, y, 10, packet)
+    out["q28"] = (bq, y, b, xq)
+    return out
+
+
+def main():
+    build_oracle(with_ref=True)
+    refs = {k: Ref(k) for k in ("f32s", "f32f", "q28")}
+    # ---- fixture A
+    T = 4800
+    params = cfg1_params()
+    ins = cfg1_inputs(T)
+    save = {"params": params}
+    for name, sig in ins.items():
+        x = np.stack([sig, -0.5 * sig]).astype(np.float32)          # L and a scaled/inverted R
+        r = run(refs, params, x, 48000.0, 48)
+        save[f"{name}_x"] = x
+        for fl in ("f32s", "f32f"):
+            save[f"{name}_{fl}_y"] = r[fl][1]
+            save[f"{name}_{fl}_state"] = r[fl][2]
+        save[f"{name}_q28_x"] = r["q28"][3]
+        save[f"{name}_q28_y"] = r["q28"][1]
+        save[f"{name}_q28_state"] = r["q28"][2]
+    save["bq_f32"] = r["f32s"][0]
+    save["bq_q28"] = r["q28"][0]
+    np.savez_compressed(os.path.join(HERE, "cfg1.npz"), **save)
+    # ---- fixture B
+    fs, Cn, T = 96000.0, 24, 960
+    params = W.eq_params("mixed", Cn, fs=fs, seed=2024)
+    x = W.inputs_f32(Cn, T)
+    r = run(refs, params, x, fs, 96)
+    np.savez_compressed(os.path.join(HERE, "mix.npz"), params=params, x=x, bq_f32=r["f32s"][0], bq_q28=r["q28"][0],
+                        f32s_y=r["f32s"][1], f32s_state=r["f32s"][2], f32f_y=r["f32f"][1], f32f_state=r["f32f"][2],
+                        q28_x=r["q28"][3], q28_y=r["q28"][1], q28_state=r["q28"][2])
+    for f in ("cfg1.npz", "mix.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol the
+header declares, the host parameter API matches the reference, and the engine refuses to
+run without a GPU (no CPU fallback).  No GPU compute here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dspi_b200 import api, layouts as L, workloads as W
+from tests.util import same_bits
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(api.LIB_PATH):
+        from dspi_b200.build import build
+        build()
+    return api.lib()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "dspi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dspi_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(api.SYMBOLS), declared ^ set(api.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_product_does_not_reference_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dspi_b200")):
+        for f in files:
+            if f.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liborc" not in src and "tests.orc" not in src and "dspi_oracle" not in src, f
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "mixed"])
+@pytest.mark.parametrize("fs", [44100.0, 48000.0, 96000.0])
+def test_host_coefficients_match_oracle_and_reference(lib, oracle, variant, fs):
+    params = W.eq_params(variant, 16, fs=fs, seed=21)
+    for q28 in (False, True):
+        p1, p2 = params.copy(), params.copy()
+        mine = api.compute_coefficients(p1, q28=q28, fs=fs)
+        theirs = np.zeros(params.shape, L.BIQUAD_Q28 if q28 else L.BIQUAD_F32)
+        oracle.eq_coeffs(q28, p2, theirs, fs)
+        assert same_bits(mine, theirs) and same_bits(p1, p2)
+
+
+def test_host_coefficients_keep_state_unless_topology_flips(lib):
+    p = np.zeros(1, L.EQ_PARAM)
+    p[0] = (0, 0, L.PEAKING, 0, 1000.0, 1.0, 3.0)
+    bq = api.compute_coefficients(p.copy(), fs=48000.0)
+    assert bq[0]["use_svf"] == 1 and bq[0]["bypass"] == 0
+    bq[0]["svic1eq"], bq[0]["svic2eq"] = 0.25, -0.5
+    p[0]["gain_db"] = 4.0                                   # same topology: state survives (dsp_pipeline.c:87-92)
+    api.compute_coefficients(p.copy(), fs=48000.0, biquads=bq)
+    assert bq[0]["svic1eq"] == np.float32(0.25)
+    p[0]["freq"] = 12000.0                                  # >= fs/7.5 -> biquad path, state cleared
+    api.compute_coefficients(p.copy(), fs=48000.0, biquads=bq)
+    assert bq[0]["use_svf"] == 0 and bq[0]["svic1eq"] == 0 and bq[0]["s1"] == 0
+    p[0]["gain_db"] = 0.0                                   # flat -> bypass, b0 = 1 (KAT, dsp_pipeline.c:62-73)
+    api.compute_coefficients(p.copy(), fs=48000.0, biquads=bq)
+    assert bq[0]["bypass"] == 1 and bq[0]["b0"] == 1.0
+
+
+def test_engine_fails_loudly_without_a_gpu(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert lib.dspi_device_count() == 0
+    with pytest.raises(api.DspiError, match="no CUDA device|fallback"):
+        api.EqEngine("f32f", 64)
+
+
+def test_bad_arguments_are_rejected(lib):
+    import ctypes as C
+    h = C.c_void_p()
+    desc = api._EqDesc(7, 64, 10, 0, 0)
+    assert lib.dspi_eq_create(C.byref(h), C.byref(desc)) == -22
+    desc = api._EqDesc(0, 64, 13, 0, 0)
+    assert lib.dspi_eq_create(C.byref(h), C.byref(desc)) == -22
+    assert lib.dspi_eq_create(None, None) == -22
+    assert b"" != lib.dspi_last_error()

@@ -1,0 +1,179 @@
+"""GPU parity: the CUDA EQ kernels (K1 float fused/strict, K2 Q28), called through the C ABI,
+against the CPU oracle on the same seeded inputs and against the committed fixtures.
+
+Bars (BASELINE.json north_star): Q28 bit-exact; float <= 1 ULP against the oracle run in the
+same arithmetic flavour (observed and asserted: 0 ULP, i.e. bit-identical)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from dspi_b200 import api, layouts as L, workloads as W      # noqa: E402
+from tests.util import load_golden, same_bits, ulp_diff      # noqa: E402
+
+FLOAT_ULP_TOL = 1      # north_star: <= 1 ULP for the float biquad/SVF path
+
+
+def _run_gpu(flavour, bq, x, n_bands=10, splits=None, ld=None):
+    """Process x [C, T] through an engine; returns (y, final biquads)."""
+    Cn, T = x.shape
+    eng = api.EqEngine(flavour, Cn, n_bands)
+    try:
+        eng.upload(bq)
+        ld = T if ld is None else ld
+        buf = torch.zeros((Cn, ld), dtype=torch.int32 if eng.q28 else torch.float32, device="cuda")
+        buf[:, :T] = torch.from_numpy(x).cuda()
+        torch.cuda.synchronize()
+        t0 = 0
+        for n in (splits or [T]):
+            eng.process_device(buf.data_ptr() + t0 * 4, n, ld)
+            t0 += n
+        eng.sync()
+        y = buf[:, :T].cpu().numpy()
+        return y, eng.download()
+    finally:
+        eng.close()
+
+
+def _oracle(oracle, flavour, bq, x, n_bands=10, packet=96):
+    b, y = bq.copy(), x.copy()
+    oracle.eq_many(flavour, b, y, n_bands, packet)
+    return y, b
+
+
+def _coeffs(variant, Cn, fs, q28, seed=5):
+    params = W.eq_params(variant, Cn, fs=fs, seed=seed)
+    return api.compute_coefficients(params, q28=q28, fs=fs)
+
+
+def _assert_float_equal(y, want):
+    d = ulp_diff(y, want)
+    assert d <= FLOAT_ULP_TOL, f"max ULP distance {d}"
+    assert d == 0, "float path is expected to be bit-identical to the same-flavour oracle"
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "f32s"])
+@pytest.mark.parametrize("variant", ["A", "B", "mixed"])
+def test_float_cascade_matches_oracle(oracle, flavour, variant):
+    fs, Cn, T = 96000.0, 256, 2048
+    bq = _coeffs(variant, Cn, fs, False)
+    x = W.inputs_f32(Cn, T)
+    x[3] = 0; x[3, 0] = 1.0            # impulse: decays through the flush-to-zero range
+    x[5] *= 1e-30
+    y, st = _run_gpu(flavour, bq, x)
+    want, wst = _oracle(oracle, flavour, bq, x)
+    _assert_float_equal(y, want)
+    assert same_bits(st, wst)
+
+
+@pytest.mark.parametrize("variant", ["A", "B", "mixed"])
+def test_q28_cascade_bit_exact(oracle, variant):
+    fs, Cn, T = 96000.0, 256, 2048
+    bq = _coeffs(variant, Cn, fs, True)
+    x = W.inputs_q28(Cn, T)
+    x[2] = np.random.default_rng(1).integers(-2**31, 2**31, T, dtype=np.int64).astype(np.int32)   # wrap-around stress
+    y, st = _run_gpu("q28", bq, x)
+    want, wst = _oracle(oracle, "q28", bq, x)
+    assert np.array_equal(y, want)
+    assert same_bits(st, wst)
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "q28"])
+@pytest.mark.parametrize("Cn,T,ld", [(1, 1, 4), (2, 48, 48), (100, 1004, 1004), (65, 1003, 1003), (130, 96, 200), (64, 33, 36)])
+def test_ragged_shapes(oracle, flavour, Cn, T, ld):
+    """empty-ish, ragged and unaligned shapes: partial groups, partial tiles, non-TMA strides"""
+    fs = 48000.0
+    q = flavour == "q28"
+    bq = _coeffs("mixed", Cn, fs, q, seed=9)
+    x = W.inputs_q28(Cn, T) if q else W.inputs_f32(Cn, T)
+    y, st = _run_gpu(flavour, bq, x, ld=ld)
+    want, wst = _oracle(oracle, flavour, bq, x, packet=48)
+    assert np.array_equal(y.view(np.uint32), want.view(np.uint32))
+    assert same_bits(st, wst)
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "f32s", "q28"])
+def test_state_carries_across_calls(oracle, flavour):
+    """packets of 96/48/odd sizes in separate launches == one launch == the oracle"""
+    fs, Cn, T = 96000.0, 128, 96 * 8 + 48 + 20
+    q = flavour == "q28"
+    bq = _coeffs("B", Cn, fs, q)
+    x = W.inputs_q28(Cn, T) if q else W.inputs_f32(Cn, T)
+    y1, st1 = _run_gpu(flavour, bq, x, ld=T)
+    y2, st2 = _run_gpu(flavour, bq, x, splits=[96] * 8 + [48, 20], ld=T)
+    want, wst = _oracle(oracle, flavour, bq, x)
+    assert np.array_equal(y1.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(y2.view(np.uint32), want.view(np.uint32))
+    assert same_bits(st1, wst) and same_bits(st2, wst)
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "f32s", "q28"])
+def test_golden_fixtures(flavour):
+    g = load_golden("mix.npz")
+    q = flavour == "q28"
+    y, st = _run_gpu(flavour, g["bq_q28" if q else "bq_f32"], g["q28_x" if q else "x"])
+    assert np.array_equal(y.view(np.uint32), g[f"{flavour}_y"].view(np.uint32))
+    assert same_bits(st, g[f"{flavour}_state"])
+    g = load_golden("cfg1.npz")
+    for sig in ("impulse", "sine", "sweep", "noise"):
+        y, st = _run_gpu(flavour, g["bq_q28" if q else "bq_f32"], g[f"{sig}_q28_x" if q else f"{sig}_x"], splits=[48] * 100)
+        assert np.array_equal(y.view(np.uint32), g[f"{sig}_{flavour}_y"].view(np.uint32)), sig
+        assert same_bits(st, g[f"{sig}_{flavour}_state"])
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "q28"])
+def test_host_path_and_set_param(oracle, flavour):
+    """dspi_eq_process_host (chunked H2D/compute/D2H) and the REQ_SET_EQ_PARAM path"""
+    fs, Cn, T = 48000.0, 192, 4096
+    q = flavour == "q28"
+    bq = _coeffs("B", Cn, fs, q)
+    x = W.inputs_q28(Cn, T) if q else W.inputs_f32(Cn, T)
+    eng = api.EqEngine(flavour, Cn)
+    pin = api.PinnedBuffer((Cn, T), np.int32 if q else np.float32)
+    try:
+        eng.upload(bq)
+        pin.array[...] = x
+        eng.process_host(pin.array)
+        want, wst = _oracle(oracle, flavour, bq, x)
+        assert np.array_equal(pin.array.view(np.uint32), want.view(np.uint32))
+        # change one band between "packets" like main.c:826-857, then keep going
+        p = np.zeros(1, L.EQ_PARAM)
+        p[0] = (0, 4, L.PEAKING, 0, 2500.0, 2.0, -5.0)
+        eng.set_param(7, p[0], fs)
+        wst2 = wst.copy()
+        row = wst2[7:8, 4]
+        oracle.eq_coeffs(q, p.copy(), row, fs)
+        wst2[7, 4] = row[0]
+        pin.array[...] = x
+        eng.process_host(pin.array)
+        want2, wst3 = _oracle(oracle, flavour, wst2, x)
+        assert np.array_equal(pin.array.view(np.uint32), want2.view(np.uint32))
+        assert same_bits(eng.download(), wst3)
+    finally:
+        pin.free()
+        eng.close()
+
+
+@pytest.mark.parametrize("flavour,Cn", [("f32f", 65536), ("q28", 32768)])
+def test_full_size_properties(flavour, Cn):
+    """BASELINE configs 2 / 4 at full channel count, checked through size-independent properties:
+    (a) every 512th channel against nothing but itself processed alone in a small engine
+    (sharding / grouping must not change a bit), (b) all-bypass coefficients are the identity."""
+    fs, T = 96000.0, 256
+    q = flavour == "q28"
+    params = W.eq_params_fast("A" if not q else "B", Cn, fs=fs, seed=3)
+    bq = api.compute_coefficients(params[::512].copy(), q28=q, fs=fs)
+    full = np.zeros((Cn, L.MAX_BANDS), L.BIQUAD_Q28 if q else L.BIQUAD_F32)
+    full["bypass"] = 1
+    full["b0"] = (1 << 28) if q else 1.0
+    full[::512] = bq
+    x = (W.inputs_q28(Cn // 512, T) if q else W.inputs_f32(Cn // 512, T))
+    xf = np.zeros((Cn, T), x.dtype)
+    xf[::512] = x
+    xf[1::512] = x                      # neighbours are bypassed: must come back untouched
+    y, _ = _run_gpu(flavour, full, xf)
+    ysmall, _ = _run_gpu(flavour, bq, x)
+    assert np.array_equal(y[::512].view(np.uint32), ysmall.view(np.uint32))
+    assert np.array_equal(y[1::512].view(np.uint32), x.view(np.uint32))
