@@ -271,6 +271,7 @@ static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaS
     a.T = T;
     a.n_bands = e->desc.n_bands;
     a.use_tma = tma_ok ? 1u : 0u;
+    if (const char *v = getenv("DSPI_DBG")) a.dbg = (uint32_t)atoi(v);
     cudaError_t err;
     if (e->desc.arith == DSPI_ARITH_Q28) err = dspi::launch_eq_q28(a, stream);
     else err = dspi::launch_eq_f32(a, e->desc.arith == DSPI_ARITH_F32_FUSED, e->cpl, stream);

@@ -28,29 +28,83 @@ namespace dspi {
 namespace {
 
 // ---------------------------------------------------------------------------------------
-// value types: float (1 channel / lane) or float2 (2 channels / lane, packed f32x2)
+// value types: float (1 channel / lane) or P2 (2 channels / lane, packed f32x2)
+//
+// P2 is an opaque 64-bit register pair driven with inline PTX: keeping the pair as ONE .b64
+// virtual register forces ptxas to hold every sample/state/coefficient packed for the whole
+// kernel.  (With P2 + the __ffma2_rn intrinsics the halves are separate 32-bit values and
+// ptxas re-packs them with two MOVs around every packed instruction.)
 // ---------------------------------------------------------------------------------------
+struct P2 { unsigned long long v; };
+
 __device__ __forceinline__ float v_mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float v_add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float v_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ float2 v_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 v_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 v_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ P2 v_mul(P2 a, P2 b)
+{
+    P2 r;
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ P2 v_add(P2 a, P2 b)
+{
+    P2 r;
+    asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ P2 v_fma(P2 a, P2 b, P2 c)
+{
+    P2 r;
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ P2 p2_pack(float lo, float hi)
+{
+    P2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void p2_unpack(P2 a, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
 
+template <typename V> __device__ __forceinline__ V v_bits(unsigned long long b);
+template <> __device__ __forceinline__ float v_bits<float>(unsigned long long b) { return __uint_as_float((unsigned)b); }
+template <> __device__ __forceinline__ P2 v_bits<P2>(unsigned long long b) { P2 r; r.v = b; return r; }
 template <typename V> __device__ __forceinline__ V v_set(float x);
 template <> __device__ __forceinline__ float v_set<float>(float x) { return x; }
-template <> __device__ __forceinline__ float2 v_set<float2>(float x) { return make_float2(x, x); }
+template <> __device__ __forceinline__ P2 v_set<P2>(float x) { return p2_pack(x, x); }
 
 // sign flip on the integer pipe (exact; a flushed-denormal operand is flushed by the consumer)
 __device__ __forceinline__ float v_neg(float a) { return __int_as_float(__float_as_int(a) ^ 0x80000000); }
-__device__ __forceinline__ float2 v_neg(float2 a) { return make_float2(v_neg(a.x), v_neg(a.y)); }
+__device__ __forceinline__ P2 v_neg(P2 a) { P2 r; r.v = a.v ^ 0x8000000080000000ull; return r; }
+
+// ptxas (12.9) contracts `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 even with --fmad=false and
+// even when the product is written as fma(a, b, -0.0) with a literal -0.0 (it folds that back to
+// a multiply first).  The strict flavour therefore forms packed products as fma(a, b, nz) where
+// nz = (-0.0, -0.0) arrives as a KERNEL PARAMETER: an exact product rounding (x + -0 == x for
+// every x, including both zeros) that the assembler cannot prove foldable.  Scalar FMUL/FADD
+// and every fused-flavour sequence are left alone by ptxas (checked in the SASS).
+template <bool FUSED> __device__ __forceinline__ float mulx(float a, float b, float) { return __fmul_rn(a, b); }
+template <bool FUSED> __device__ __forceinline__ P2 mulx(P2 a, P2 b, P2 nz)
+{
+    if constexpr (FUSED) return v_mul(a, b);
+    else return v_fma(a, b, nz);
+}
 
 // a*b + c: one rounding (FUSED) or two (strict)
 template <bool FUSED, typename V>
-__device__ __forceinline__ V madd(V a, V b, V c)
+__device__ __forceinline__ V madd(V a, V b, V c, V nz)
 {
     if constexpr (FUSED) return v_fma(a, b, c);
-    else return v_add(v_mul(a, b), c);
+    else return v_add(mulx<false>(a, b, nz), c);
+}
+template <bool FUSED>
+__device__ __forceinline__ float madd(float a, float b, float c)
+{
+    if constexpr (FUSED) return __fmaf_rn(a, b, c);
+    else return __fadd_rn(__fmul_rn(a, b), c);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -60,16 +114,16 @@ __device__ __forceinline__ V madd(V a, V b, V c)
 // TDF2 biquad, dsp_pipeline.c:354-360.  c = {b0, b1, b2, -a1, -a2}
 //   out = b0*in + s1;  s1 = b1*in - a1*out + s2;  s2 = b2*in - a2*out
 template <bool FUSED, int N, typename V>
-__device__ __forceinline__ void tdf2_tile(V (&x)[N], const V (&c)[6], V &s1, V &s2)
+__device__ __forceinline__ void tdf2_tile(V (&x)[N], const V (&c)[6], V &s1, V &s2, const V nz)
 {
 #pragma unroll
     for (int i = 0; i < N; i++) {
         const V in = x[i];
-        const V out = madd<FUSED>(c[0], in, s1);
-        const V m = v_mul(c[3], out);                    // -(a1*out), exact negation of the reference's product
-        s1 = v_add(madd<FUSED>(c[1], in, m), s2);
-        const V n = v_mul(c[4], out);
-        s2 = madd<FUSED>(c[2], in, n);
+        const V out = madd<FUSED>(c[0], in, s1, nz);
+        const V m = mulx<FUSED>(c[3], out, nz);          // -(a1*out), exact negation of the reference's product
+        s1 = v_add(madd<FUSED>(c[1], in, m, nz), s2);
+        const V n = mulx<FUSED>(c[4], out, nz);
+        s2 = madd<FUSED>(c[2], in, n, nz);
         x[i] = out;
     }
 }
@@ -84,7 +138,7 @@ __device__ __forceinline__ void tdf2_tile(V (&x)[N], const V (&c)[6], V &s1, V &
 enum { kMixLP = 2, kMixHP = 3, kMixPK = 4, kMixSH = 5 };
 
 template <bool FUSED, int MIX, int N, typename V>
-__device__ __forceinline__ void svf_tile(V (&x)[N], const V (&c)[6], V &ic1, V &ic2)
+__device__ __forceinline__ void svf_tile(V (&x)[N], const V (&c)[6], V &ic1, V &ic2, const V nz)
 {
     static_assert(N % 2 == 0, "SVF tile processes sample pairs");
     const V kN1 = v_set<V>(-1.0f), kN2 = v_set<V>(-2.0f), kP2 = v_set<V>(2.0f);
@@ -94,49 +148,49 @@ __device__ __forceinline__ void svf_tile(V (&x)[N], const V (&c)[6], V &ic1, V &
         {   // ---- state positive on entry, negated on exit
             const V in = x[i];
             const V v3 = v_fma(ic2, kN1, in);                       // in - ic2 (exact product)
-            const V p = v_mul(c[1], v3);
+            const V p = mulx<FUSED>(c[1], v3, nz);
             V t, v1, v2;
             if constexpr (FUSED) {
                 t = v_fma(c[1], ic1, ic2);                          // a2*ic1 + ic2
                 v1 = v_fma(c[0], ic1, p);                           // a1*ic1 + a2*v3
                 v2 = v_fma(c[2], v3, t);
             } else {
-                t = v_add(ic2, v_mul(c[1], ic1));
-                v1 = v_add(v_mul(c[0], ic1), p);
-                v2 = v_add(t, v_mul(c[2], v3));
+                t = v_add(ic2, mulx<FUSED>(c[1], ic1, nz));
+                v1 = v_add(mulx<FUSED>(c[0], ic1, nz), p);
+                v2 = v_add(t, mulx<FUSED>(c[2], v3, nz));
             }
             ic1 = v_fma(v1, kN2, ic1);                              // -(2*v1 - ic1)
             ic2 = v_fma(v2, kN2, ic2);
             if constexpr (MIX == kMixLP) x[i] = v2;
-            else if constexpr (MIX == kMixPK) x[i] = madd<FUSED>(c[4], v1, in);
-            else if constexpr (MIX == kMixHP) x[i] = v_fma(v2, kN1, madd<FUSED>(c[4], v1, in));
+            else if constexpr (MIX == kMixPK) x[i] = madd<FUSED>(c[4], v1, in, nz);
+            else if constexpr (MIX == kMixHP) x[i] = v_fma(v2, kN1, madd<FUSED>(c[4], v1, in, nz));
             else {
-                const V q = v_mul(c[4], v1);
-                x[i] = madd<FUSED>(c[5], v2, madd<FUSED>(c[3], in, q));
+                const V q = mulx<FUSED>(c[4], v1, nz);
+                x[i] = madd<FUSED>(c[5], v2, madd<FUSED>(c[3], in, q, nz), nz);
             }
         }
         {   // ---- state negated on entry (n1 = -ic1, n2 = -ic2), positive on exit
             const V in = x[i + 1];
             const V v3 = v_add(in, ic2);                            // in - ic2
-            const V p = v_mul(c[1], v3);
+            const V p = mulx<FUSED>(c[1], v3, nz);
             V nt, v1, nv2;
             if constexpr (FUSED) {
                 nt = v_fma(c[1], ic1, ic2);                         // -(a2*ic1 + ic2)
                 v1 = v_fma(na1, ic1, p);                            // a1*ic1 + a2*v3
                 nv2 = v_fma(na3, v3, nt);                           // -v2
             } else {
-                nt = v_add(ic2, v_mul(c[1], ic1));
-                v1 = v_add(v_mul(na1, ic1), p);
-                nv2 = v_add(nt, v_mul(na3, v3));
+                nt = v_add(ic2, mulx<FUSED>(c[1], ic1, nz));
+                v1 = v_add(mulx<FUSED>(na1, ic1, nz), p);
+                nv2 = v_add(nt, mulx<FUSED>(na3, v3, nz));
             }
             ic1 = v_fma(v1, kP2, ic1);                              // 2*v1 - ic1
             ic2 = v_fma(nv2, kN2, ic2);                             // 2*v2 - ic2
-            if constexpr (MIX == kMixLP) x[i + 1] = v_mul(nv2, kN1);
-            else if constexpr (MIX == kMixPK) x[i + 1] = madd<FUSED>(c[4], v1, in);
-            else if constexpr (MIX == kMixHP) x[i + 1] = v_add(madd<FUSED>(c[4], v1, in), nv2);
+            if constexpr (MIX == kMixLP) x[i + 1] = mulx<FUSED>(nv2, kN1, nz);
+            else if constexpr (MIX == kMixPK) x[i + 1] = madd<FUSED>(c[4], v1, in, nz);
+            else if constexpr (MIX == kMixHP) x[i + 1] = v_add(madd<FUSED>(c[4], v1, in, nz), nv2);
             else {
-                const V q = v_mul(c[4], v1);
-                x[i + 1] = madd<FUSED>(nm2, nv2, madd<FUSED>(c[3], in, q));
+                const V q = mulx<FUSED>(c[4], v1, nz);
+                x[i + 1] = madd<FUSED>(nm2, nv2, madd<FUSED>(c[3], in, q, nz), nz);
             }
         }
     }
@@ -194,12 +248,13 @@ template <typename V> struct Lanes;
 template <> struct Lanes<float> {
     static constexpr int CPL = 1;
     __device__ static __forceinline__ float get(float v, int) { return v; }
-    __device__ static __forceinline__ void put(float &v, int, float x) { v = x; }
 };
-template <> struct Lanes<float2> {
+// build a value from per-half scalars (h = 0: channel `lane`, h = 1: channel `lane + 32`)
+__device__ __forceinline__ void v_make(float &v, const float (&part)[1]) { v = part[0]; }
+__device__ __forceinline__ void v_make(P2 &v, const float (&part)[2]) { v = p2_pack(part[0], part[1]); }
+template <> struct Lanes<P2> {
     static constexpr int CPL = 2;
-    __device__ static __forceinline__ float get(float2 v, int h) { return h ? v.y : v.x; }
-    __device__ static __forceinline__ void put(float2 &v, int h, float x) { if (h) v.y = x; else v.x = x; }
+    __device__ static __forceinline__ float get(P2 v, int h) { float lo, hi; p2_unpack(v, lo, hi); return h ? hi : lo; }
 };
 
 constexpr int kTileT = 32;          // samples per shared-memory tile row: 128 B == swizzle span
@@ -209,7 +264,7 @@ constexpr int kStages = 3;
 template <typename V, bool FUSED, int NB>
 __global__ void __launch_bounds__(256 * 2 / Lanes<V>::CPL, 1)
 eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samples, uint32_t ld, V *__restrict__ coef,
-              const uint64_t *__restrict__ modes, uint32_t n_groups, uint32_t n_rows, uint32_t T, uint32_t nb_active, uint32_t use_tma)
+              const uint64_t *__restrict__ modes, uint32_t n_groups, uint32_t n_rows, uint32_t T, uint32_t nb_active, uint32_t use_tma, uint32_t dbg, unsigned long long nz_bits)
 {
     constexpr int CPL = Lanes<V>::CPL;
     constexpr int kRows = 32 * CPL;
@@ -232,6 +287,7 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
     }
     __syncwarp();
 
+    const V nz = v_bits<V>(nz_bits);                            // (-0.0, -0.0): see mulx()
     const int c0 = g * kRows;                                   // first channel (row) of this group
     const uint32_t ntiles = (T + kTileT - 1) / kTileT;
 
@@ -240,7 +296,8 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
         mbar_arrive_expect_tx(&full[s], kStageBytes);
         tma_load_2d(my_smem + s * kStageBytes, &tmap, &full[s], tile * kTileT, c0);
     };
-    if (use_tma && lane == 0)
+    const bool mem_on = !(dbg & 2u);                            // diagnostics: DSPI_DBG=2 runs the arithmetic without HBM traffic
+    if (use_tma && mem_on && lane == 0)
         for (uint32_t s = 0; s + 1 < kStages && s < ntiles; s++) issue_load(s);
 
     // ---- coefficients, state and modes of every band -> registers ---------------------
@@ -272,7 +329,7 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
         const uint32_t s = tile % kStages;
         uint8_t *buf = my_smem + s * kStageBytes;
         if (use_tma) {
-            mbar_wait(&full[s], (tile / kStages) & 1);
+            if (mem_on) mbar_wait(&full[s], (tile / kStages) & 1);
         } else {                                                // plain-load fallback (odd strides / unaligned bases)
             const uint32_t t = tile * kTileT + lane;
             for (int r = 0; r < kRows; r++) {
@@ -299,40 +356,50 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
                 q[h][1] = *reinterpret_cast<const float4 *>(row + (((2 * sub + 1) << 4) ^ sw));
             }
 #pragma unroll
-            for (int h = 0; h < CPL; h++) {
-                Lanes<V>::put(x[0], h, q[h][0].x); Lanes<V>::put(x[1], h, q[h][0].y);
-                Lanes<V>::put(x[2], h, q[h][0].z); Lanes<V>::put(x[3], h, q[h][0].w);
-                Lanes<V>::put(x[4], h, q[h][1].x); Lanes<V>::put(x[5], h, q[h][1].y);
-                Lanes<V>::put(x[6], h, q[h][1].z); Lanes<V>::put(x[7], h, q[h][1].w);
+            for (int i = 0; i < kSub; i++) {
+                float part[CPL];
+#pragma unroll
+                for (int h = 0; h < CPL; h++) {
+                    const float4 &qq = q[h][i >> 2];
+                    part[h] = (i & 3) == 0 ? qq.x : (i & 3) == 1 ? qq.y : (i & 3) == 2 ? qq.z : qq.w;
+                }
+                v_make(x[i], part);
             }
 
 #pragma unroll
             for (int b = 0; b < NB; b++) {
-                if (b >= (int)nb_active) break;
+                if (b >= (int)nb_active || (dbg & 1u)) break;     // DSPI_DBG=1: data path only
                 const uint32_t m = (uint32_t)(mode_w >> (4 * b)) & 15u;
                 if (((uni >> b) & 1u) && nvalid == kSub) {
                     switch (m) {                                // warp-uniform branch
-                    case kModeTdf2:  tdf2_tile<FUSED>(x, c[b], st[b][0], st[b][1]); break;
-                    case kModeSvfLP: svf_tile<FUSED, kMixLP>(x, c[b], st[b][0], st[b][1]); break;
-                    case kModeSvfHP: svf_tile<FUSED, kMixHP>(x, c[b], st[b][0], st[b][1]); break;
-                    case kModeSvfPK: svf_tile<FUSED, kMixPK>(x, c[b], st[b][0], st[b][1]); break;
-                    case kModeSvfSH: svf_tile<FUSED, kMixSH>(x, c[b], st[b][0], st[b][1]); break;
+                    case kModeTdf2:  tdf2_tile<FUSED>(x, c[b], st[b][0], st[b][1], nz); break;
+                    case kModeSvfLP: svf_tile<FUSED, kMixLP>(x, c[b], st[b][0], st[b][1], nz); break;
+                    case kModeSvfHP: svf_tile<FUSED, kMixHP>(x, c[b], st[b][0], st[b][1], nz); break;
+                    case kModeSvfPK: svf_tile<FUSED, kMixPK>(x, c[b], st[b][0], st[b][1], nz); break;
+                    case kModeSvfSH: svf_tile<FUSED, kMixSH>(x, c[b], st[b][0], st[b][1], nz); break;
                     default: break;                             // bypassed band: dsp_pipeline.c:288
                     }
                 } else {
-                    float xs[kSub];
+                    float xs[CPL][kSub], ns0[CPL], ns1[CPL];
 #pragma unroll
                     for (int h = 0; h < CPL; h++) {
 #pragma unroll
-                        for (int i = 0; i < kSub; i++) xs[i] = Lanes<V>::get(x[i], h);
+                        for (int i = 0; i < kSub; i++) xs[h][i] = Lanes<V>::get(x[i], h);
                         const uint32_t mh = (uint32_t)(mode_h[h] >> (4 * b)) & 15u;
-                        const float2 ns = slow_band<FUSED>(xs, nvalid, mh, Lanes<V>::get(c[b][0], h), Lanes<V>::get(c[b][1], h),
+                        const float2 ns = slow_band<FUSED>(xs[h], nvalid, mh, Lanes<V>::get(c[b][0], h), Lanes<V>::get(c[b][1], h),
                                                            Lanes<V>::get(c[b][2], h), Lanes<V>::get(c[b][3], h), Lanes<V>::get(c[b][4], h),
                                                            Lanes<V>::get(c[b][5], h), Lanes<V>::get(st[b][0], h), Lanes<V>::get(st[b][1], h));
-                        Lanes<V>::put(st[b][0], h, ns.x);
-                        Lanes<V>::put(st[b][1], h, ns.y);
+                        ns0[h] = ns.x;
+                        ns1[h] = ns.y;
+                    }
+                    v_make(st[b][0], ns0);
+                    v_make(st[b][1], ns1);
 #pragma unroll
-                        for (int i = 0; i < kSub; i++) Lanes<V>::put(x[i], h, xs[i]);
+                    for (int i = 0; i < kSub; i++) {
+                        float part[CPL];
+#pragma unroll
+                        for (int h = 0; h < CPL; h++) part[h] = xs[h][i];
+                        v_make(x[i], part);
                     }
                 }
             }
@@ -350,7 +417,7 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
         if (use_tma) {
             fence_proxy_async_smem();                           // my smem writes -> async proxy
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && mem_on) {
                 tma_store_2d(&tmap, buf, tile * kTileT, c0);
                 tma_store_commit();
                 const uint32_t nxt = tile + kStages - 1;        // refill the buffer stored one iteration ago
@@ -396,7 +463,7 @@ cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
     }
     const uint32_t n_groups = a.n_groups;
     const uint32_t grid = (n_groups + kWarps - 1) / kWarps;
-    kern<<<grid, kWarps * 32, smem, stream>>>(a.tmap, (float *)a.samples, a.ld, (V *)a.coef, a.modes, n_groups, a.n_rows, a.T, a.n_bands, a.use_tma);
+    kern<<<grid, kWarps * 32, smem, stream>>>(a.tmap, (float *)a.samples, a.ld, (V *)a.coef, a.modes, n_groups, a.n_rows, a.T, a.n_bands, a.use_tma, a.dbg, 0x8000000080000000ull);
     return cudaGetLastError();
 }
 
@@ -411,7 +478,7 @@ cudaError_t launch_nb(const EqLaunch &a, cudaStream_t stream)
 
 cudaError_t launch_eq_f32(const EqLaunch &a, bool fused, int cpl, cudaStream_t stream)
 {
-    if (cpl == 2) return fused ? launch_nb<float2, true>(a, stream) : launch_nb<float2, false>(a, stream);
+    if (cpl == 2) return fused ? launch_nb<P2, true>(a, stream) : launch_nb<P2, false>(a, stream);
     return fused ? launch_nb<float, true>(a, stream) : launch_nb<float, false>(a, stream);
 }
 

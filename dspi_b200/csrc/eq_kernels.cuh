@@ -28,6 +28,7 @@ struct EqLaunch {
     uint32_t T;
     uint32_t n_bands;
     uint32_t use_tma;
+    uint32_t dbg;          // diagnostics only (env DSPI_DBG): 1 = skip arithmetic, 2 = skip HBM traffic
 };
 
 // K1 — float cascade.  cpl: channels per lane (1 scalar FFMA, 2 packed FFMA2)

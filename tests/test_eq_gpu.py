@@ -50,6 +50,11 @@ def _coeffs(variant, Cn, fs, q28, seed=5):
 
 def _assert_float_equal(y, want):
     d = ulp_diff(y, want)
+    if d:
+        bad = np.argwhere(y.view(np.uint32) != want.view(np.uint32))
+        c, t = bad[0]
+        print(f"first mismatch at channel {c} sample {t}: gpu {y[c, t]!r} oracle {want[c, t]!r}; "
+              f"{len(bad)} mismatching samples in channels {sorted(set(bad[:, 0].tolist()))[:16]}")
     assert d <= FLOAT_ULP_TOL, f"max ULP distance {d}"
     assert d == 0, "float path is expected to be bit-identical to the same-flavour oracle"
 
