@@ -114,7 +114,7 @@ __device__ __forceinline__ float madd(float a, float b, float c)
 // TDF2 biquad, dsp_pipeline.c:354-360.  c = {b0, b1, b2, -a1, -a2}
 //   out = b0*in + s1;  s1 = b1*in - a1*out + s2;  s2 = b2*in - a2*out
 template <bool FUSED, int N, typename V>
-__device__ __forceinline__ void tdf2_tile(V (&x)[N], const V (&c)[6], V &s1, V &s2, const V nz)
+__device__ __forceinline__ void tdf2_tile(const V (&x)[N], V (&y)[N], const V (&c)[6], V &s1, V &s2, const V nz)
 {
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -124,7 +124,7 @@ __device__ __forceinline__ void tdf2_tile(V (&x)[N], const V (&c)[6], V &s1, V &
         s1 = v_add(madd<FUSED>(c[1], in, m, nz), s2);
         const V n = mulx<FUSED>(c[4], out, nz);
         s2 = madd<FUSED>(c[2], in, n, nz);
-        x[i] = out;
+        y[i] = out;
     }
 }
 
@@ -138,7 +138,7 @@ __device__ __forceinline__ void tdf2_tile(V (&x)[N], const V (&c)[6], V &s1, V &
 enum { kMixLP = 2, kMixHP = 3, kMixPK = 4, kMixSH = 5 };
 
 template <bool FUSED, int MIX, int N, typename V>
-__device__ __forceinline__ void svf_tile(V (&x)[N], const V (&c)[6], V &ic1, V &ic2, const V nz)
+__device__ __forceinline__ void svf_tile(const V (&x)[N], V (&y)[N], const V (&c)[6], V &ic1, V &ic2, const V nz)
 {
     static_assert(N % 2 == 0, "SVF tile processes sample pairs");
     const V kN1 = v_set<V>(-1.0f), kN2 = v_set<V>(-2.0f), kP2 = v_set<V>(2.0f);
@@ -161,12 +161,12 @@ __device__ __forceinline__ void svf_tile(V (&x)[N], const V (&c)[6], V &ic1, V &
             }
             ic1 = v_fma(v1, kN2, ic1);                              // -(2*v1 - ic1)
             ic2 = v_fma(v2, kN2, ic2);
-            if constexpr (MIX == kMixLP) x[i] = v2;
-            else if constexpr (MIX == kMixPK) x[i] = madd<FUSED>(c[4], v1, in, nz);
-            else if constexpr (MIX == kMixHP) x[i] = v_fma(v2, kN1, madd<FUSED>(c[4], v1, in, nz));
+            if constexpr (MIX == kMixLP) y[i] = v2;
+            else if constexpr (MIX == kMixPK) y[i] = madd<FUSED>(c[4], v1, in, nz);
+            else if constexpr (MIX == kMixHP) y[i] = v_fma(v2, kN1, madd<FUSED>(c[4], v1, in, nz));
             else {
                 const V q = mulx<FUSED>(c[4], v1, nz);
-                x[i] = madd<FUSED>(c[5], v2, madd<FUSED>(c[3], in, q, nz), nz);
+                y[i] = madd<FUSED>(c[5], v2, madd<FUSED>(c[3], in, q, nz), nz);
             }
         }
         {   // ---- state negated on entry (n1 = -ic1, n2 = -ic2), positive on exit
@@ -185,12 +185,12 @@ __device__ __forceinline__ void svf_tile(V (&x)[N], const V (&c)[6], V &ic1, V &
             }
             ic1 = v_fma(v1, kP2, ic1);                              // 2*v1 - ic1
             ic2 = v_fma(nv2, kN2, ic2);                             // 2*v2 - ic2
-            if constexpr (MIX == kMixLP) x[i + 1] = mulx<FUSED>(nv2, kN1, nz);
-            else if constexpr (MIX == kMixPK) x[i + 1] = madd<FUSED>(c[4], v1, in, nz);
-            else if constexpr (MIX == kMixHP) x[i + 1] = v_add(madd<FUSED>(c[4], v1, in, nz), nv2);
+            if constexpr (MIX == kMixLP) y[i + 1] = mulx<FUSED>(nv2, kN1, nz);
+            else if constexpr (MIX == kMixPK) y[i + 1] = madd<FUSED>(c[4], v1, in, nz);
+            else if constexpr (MIX == kMixHP) y[i + 1] = v_add(madd<FUSED>(c[4], v1, in, nz), nv2);
             else {
                 const V q = mulx<FUSED>(c[4], v1, nz);
-                x[i + 1] = madd<FUSED>(nm2, nv2, madd<FUSED>(c[3], in, q, nz), nz);
+                y[i + 1] = madd<FUSED>(nm2, nv2, madd<FUSED>(c[3], in, q, nz), nz);
             }
         }
     }
@@ -312,7 +312,10 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
     }
     uint64_t mode_h[CPL];
 #pragma unroll
-    for (int h = 0; h < CPL; h++) mode_h[h] = modes[(size_t)g * kRows + h * 32 + lane];
+    for (int h = 0; h < CPL; h++) {
+        mode_h[h] = modes[(size_t)g * kRows + h * 32 + lane];
+        if (nb_active < 16) mode_h[h] &= (1ull << (4 * nb_active)) - 1;          // bands >= nb_active are not processed
+    }
     const uint64_t mode_w = __shfl_sync(0xffffffffu, mode_h[0], 0);     // warp-uniform candidate
     uint32_t uni = 0;                                                   // bit b: band b has one topology in this warp
 #pragma unroll
@@ -322,6 +325,15 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
         for (int h = 0; h < CPL; h++) same = same && (((mode_h[h] ^ mode_w) >> (4 * b)) & 15) == 0;
         if (__all_sync(0xffffffffu, same)) uni |= 1u << b;
     }
+
+    // all NB bands active and TDF2 in every lane -> straight-line path
+    uint64_t want = 0;
+#pragma unroll
+    for (int b = 0; b < NB; b++) want |= (uint64_t)kModeTdf2 << (4 * b);
+    bool mine = nb_active == NB;
+#pragma unroll
+    for (int h = 0; h < CPL; h++) mine = mine && ((mode_h[h] & ((1ull << (4 * NB)) - 1)) == want);
+    const bool all_tdf2 = __all_sync(0xffffffffu, mine);
 
     // ---- stream the tiles ----------------------------------------------------------------
     const uint32_t sw = (lane & 7) << 4;                        // 128B-swizzle XOR for this lane's rows
@@ -366,40 +378,58 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
                 v_make(x[i], part);
             }
 
+            if (dbg & 1u) {
+                // DSPI_DBG=1: data path only
+            } else if (all_tdf2 && nvalid == kSub) {
+                // every band of every channel of this warp is a TDF2 biquad: one straight-line block,
+                // no dispatch, the scheduler overlaps the bands (wavefront over band x sample)
+                V y[kSub];
 #pragma unroll
-            for (int b = 0; b < NB; b++) {
-                if (b >= (int)nb_active || (dbg & 1u)) break;     // DSPI_DBG=1: data path only
-                const uint32_t m = (uint32_t)(mode_w >> (4 * b)) & 15u;
-                if (((uni >> b) & 1u) && nvalid == kSub) {
-                    switch (m) {                                // warp-uniform branch
-                    case kModeTdf2:  tdf2_tile<FUSED>(x, c[b], st[b][0], st[b][1], nz); break;
-                    case kModeSvfLP: svf_tile<FUSED, kMixLP>(x, c[b], st[b][0], st[b][1], nz); break;
-                    case kModeSvfHP: svf_tile<FUSED, kMixHP>(x, c[b], st[b][0], st[b][1], nz); break;
-                    case kModeSvfPK: svf_tile<FUSED, kMixPK>(x, c[b], st[b][0], st[b][1], nz); break;
-                    case kModeSvfSH: svf_tile<FUSED, kMixSH>(x, c[b], st[b][0], st[b][1], nz); break;
-                    default: break;                             // bypassed band: dsp_pipeline.c:288
-                    }
-                } else {
-                    float xs[CPL][kSub], ns0[CPL], ns1[CPL];
+                for (int b = 0; b < NB; b += 2) {
+                    tdf2_tile<FUSED>(x, y, c[b], st[b][0], st[b][1], nz);
+                    tdf2_tile<FUSED>(y, x, c[b + 1], st[b + 1][0], st[b + 1][1], nz);
+                }
+            } else {
+                V y[kSub];
 #pragma unroll
-                    for (int h = 0; h < CPL; h++) {
+                for (int b = 0; b < NB; b++) {
+                    // ping-pong between x and y so no case has to move its results back
+                    V(&in)[kSub] = (b & 1) ? y : x;
+                    V(&out)[kSub] = (b & 1) ? x : y;
+                    const uint32_t m = (b < (int)nb_active) ? ((uint32_t)(mode_w >> (4 * b)) & 15u) : kModeBypass;
+                    const bool fast = (((uni >> b) & 1u) || b >= (int)nb_active) && nvalid == kSub;
+                    if (fast) {
+                        if (m == kModeTdf2) tdf2_tile<FUSED>(in, out, c[b], st[b][0], st[b][1], nz);
+                        else if (m == kModeSvfPK) svf_tile<FUSED, kMixPK>(in, out, c[b], st[b][0], st[b][1], nz);
+                        else if (m == kModeSvfSH) svf_tile<FUSED, kMixSH>(in, out, c[b], st[b][0], st[b][1], nz);
+                        else if (m == kModeSvfLP) svf_tile<FUSED, kMixLP>(in, out, c[b], st[b][0], st[b][1], nz);
+                        else if (m == kModeSvfHP) svf_tile<FUSED, kMixHP>(in, out, c[b], st[b][0], st[b][1], nz);
+                        else {                                      // bypassed band: dsp_pipeline.c:288
 #pragma unroll
-                        for (int i = 0; i < kSub; i++) xs[h][i] = Lanes<V>::get(x[i], h);
-                        const uint32_t mh = (uint32_t)(mode_h[h] >> (4 * b)) & 15u;
-                        const float2 ns = slow_band<FUSED>(xs[h], nvalid, mh, Lanes<V>::get(c[b][0], h), Lanes<V>::get(c[b][1], h),
-                                                           Lanes<V>::get(c[b][2], h), Lanes<V>::get(c[b][3], h), Lanes<V>::get(c[b][4], h),
-                                                           Lanes<V>::get(c[b][5], h), Lanes<V>::get(st[b][0], h), Lanes<V>::get(st[b][1], h));
-                        ns0[h] = ns.x;
-                        ns1[h] = ns.y;
-                    }
-                    v_make(st[b][0], ns0);
-                    v_make(st[b][1], ns1);
+                            for (int i = 0; i < kSub; i++) out[i] = in[i];
+                        }
+                    } else {
+                        float xs[CPL][kSub], ns0[CPL], ns1[CPL];
 #pragma unroll
-                    for (int i = 0; i < kSub; i++) {
-                        float part[CPL];
+                        for (int h = 0; h < CPL; h++) {
 #pragma unroll
-                        for (int h = 0; h < CPL; h++) part[h] = xs[h][i];
-                        v_make(x[i], part);
+                            for (int i = 0; i < kSub; i++) xs[h][i] = Lanes<V>::get(in[i], h);
+                            const uint32_t mh = (uint32_t)(mode_h[h] >> (4 * b)) & 15u;
+                            const float2 ns = slow_band<FUSED>(xs[h], nvalid, mh, Lanes<V>::get(c[b][0], h), Lanes<V>::get(c[b][1], h),
+                                                               Lanes<V>::get(c[b][2], h), Lanes<V>::get(c[b][3], h), Lanes<V>::get(c[b][4], h),
+                                                               Lanes<V>::get(c[b][5], h), Lanes<V>::get(st[b][0], h), Lanes<V>::get(st[b][1], h));
+                            ns0[h] = ns.x;
+                            ns1[h] = ns.y;
+                        }
+                        v_make(st[b][0], ns0);
+                        v_make(st[b][1], ns1);
+#pragma unroll
+                        for (int i = 0; i < kSub; i++) {
+                            float part[CPL];
+#pragma unroll
+                            for (int h = 0; h < CPL; h++) part[h] = xs[h][i];
+                            v_make(out[i], part);
+                        }
                     }
                 }
             }
