@@ -22,11 +22,19 @@ SYMBOLS = [
     "dspi_eq_create", "dspi_eq_destroy", "dspi_eq_upload_biquads", "dspi_eq_download_biquads", "dspi_eq_set_param",
     "dspi_eq_process_device", "dspi_eq_process_host", "dspi_eq_sync", "dspi_eq_stream", "dspi_eq_launch_count",
     "dspi_host_alloc", "dspi_host_free",
+    "dspi_chain_create", "dspi_chain_destroy", "dspi_chain_set_params", "dspi_chain_upload_biquads", "dspi_chain_download_biquads",
+    "dspi_chain_reset_state", "dspi_chain_process_host", "dspi_chain_process_device", "dspi_chain_sync", "dspi_chain_stream",
+    "dspi_chain_launch_count", "dspi_delay_samples",
 ]
 
 
 class DspiError(RuntimeError):
     pass
+
+
+class _ChainDesc(C.Structure):
+    _fields_ = [("arith", C.c_uint32), ("n_instances", C.c_uint32), ("n_bands", C.c_uint32),
+                ("device", C.c_int32), ("max_frames", C.c_uint32)]
 
 
 class _EqDesc(C.Structure):
@@ -62,6 +70,21 @@ def lib():
         h.dspi_eq_stream.restype = vp
         h.dspi_eq_launch_count.argtypes = [vp]
         h.dspi_eq_launch_count.restype = C.c_uint64
+        h.dspi_chain_create.argtypes = [C.POINTER(vp), C.POINTER(_ChainDesc)]
+        h.dspi_chain_destroy.argtypes = [vp]
+        h.dspi_chain_set_params.argtypes = [vp, u32, u32, vp]
+        h.dspi_chain_upload_biquads.argtypes = [vp, u32, u32, vp]
+        h.dspi_chain_download_biquads.argtypes = [vp, u32, u32, vp]
+        h.dspi_chain_reset_state.argtypes = [vp]
+        h.dspi_chain_process_host.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
+        h.dspi_chain_process_device.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
+        h.dspi_chain_sync.argtypes = [vp]
+        h.dspi_chain_stream.argtypes = [vp]
+        h.dspi_chain_stream.restype = vp
+        h.dspi_chain_launch_count.argtypes = [vp]
+        h.dspi_chain_launch_count.restype = C.c_uint64
+        h.dspi_delay_samples.argtypes = [C.c_float, C.c_float, C.c_int]
+        h.dspi_delay_samples.restype = C.c_int32
         h.dspi_host_alloc.argtypes = [C.c_size_t]
         h.dspi_host_alloc.restype = vp
         h.dspi_host_free.argtypes = [vp]
@@ -170,3 +193,78 @@ class EqEngine:
     @property
     def launch_count(self):
         return int(lib().dspi_eq_launch_count(self._h))
+
+
+class ChainEngine:
+    """Many independent DSPi device instances, whole signal chain (``dspi_chain_*``)."""
+
+    def __init__(self, arith, n_instances, max_frames, n_bands=L.NUM_BANDS, device=0):
+        self.arith = ARITH[arith] if isinstance(arith, str) else int(arith)
+        self.n_instances, self.max_frames, self.device = int(n_instances), int(max_frames), int(device)
+        self._h = C.c_void_p()
+        desc = _ChainDesc(self.arith, self.n_instances, int(n_bands), self.device, self.max_frames)
+        _check(lib().dspi_chain_create(C.byref(self._h), C.byref(desc)))
+
+    def close(self):
+        if self._h:
+            lib().dspi_chain_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params, inst0=0):
+        p = np.ascontiguousarray(params)
+        assert p.dtype == L.CHAIN_PARAMS_F32 and p.ndim == 1
+        _check(lib().dspi_chain_set_params(self._h, inst0, p.shape[0], p.ctypes.data))
+
+    def upload_biquads(self, biquads, inst0=0):
+        b = np.ascontiguousarray(biquads)
+        assert b.dtype == L.BIQUAD_F32 and b.shape[1:] == (L.CHAIN_EQ_CHANNELS, L.MAX_BANDS)
+        _check(lib().dspi_chain_upload_biquads(self._h, inst0, b.shape[0], b.ctypes.data))
+
+    def download_biquads(self, n=None, inst0=0):
+        n = self.n_instances - inst0 if n is None else n
+        out = np.zeros((n, L.CHAIN_EQ_CHANNELS, L.MAX_BANDS), L.BIQUAD_F32)
+        _check(lib().dspi_chain_download_biquads(self._h, inst0, n, out.ctypes.data))
+        return out
+
+    def reset_state(self):
+        _check(lib().dspi_chain_reset_state(self._h))
+
+    def process_host(self, pcm, bit_depth, n_packets, frames_per_packet, want_spdif=True, want_pdm=True, want_status=True):
+        """``pcm``: uint8 [n_instances, n_frames * bytes_per_frame].  Returns (spdif, pdm, status)."""
+        F = n_packets * frames_per_packet
+        pcm = np.ascontiguousarray(pcm)
+        assert pcm.dtype == np.uint8 and pcm.shape == (self.n_instances, F * (6 if bit_depth == 24 else 4))
+        spdif = np.zeros((self.n_instances, 4, F, 2), np.int32) if want_spdif else None
+        pdm = np.zeros((self.n_instances, F, 8), np.uint32) if want_pdm else None
+        status = np.zeros(self.n_instances, L.STATUS) if want_status else None
+        _check(lib().dspi_chain_process_host(self._h, pcm.ctypes.data, bit_depth, n_packets, frames_per_packet,
+                                             spdif.ctypes.data if want_spdif else None, pdm.ctypes.data if want_pdm else None,
+                                             status.ctypes.data if want_status else None))
+        return spdif, pdm, status
+
+    def process_device(self, pcm_ptr, bit_depth, n_packets, frames_per_packet, spdif_ptr=0, pdm_ptr=0, status_ptr=0):
+        _check(lib().dspi_chain_process_device(self._h, C.c_void_p(int(pcm_ptr)), bit_depth, n_packets, frames_per_packet,
+                                               C.c_void_p(int(spdif_ptr)) if spdif_ptr else None,
+                                               C.c_void_p(int(pdm_ptr)) if pdm_ptr else None,
+                                               C.c_void_p(int(status_ptr)) if status_ptr else None))
+
+    def sync(self):
+        _check(lib().dspi_chain_sync(self._h))
+
+    @property
+    def stream(self):
+        return lib().dspi_chain_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(lib().dspi_chain_launch_count(self._h))
+
+
+def delay_samples(delay_ms, fs, is_last=False):
+    return int(lib().dspi_delay_samples(delay_ms, fs, 1 if is_last else 0))

@@ -49,6 +49,14 @@ constexpr int kHostBufs = 3;
 
 }  // namespace
 
+namespace dspi {
+char *error_buffer(size_t *cap)
+{
+    *cap = sizeof(g_err);
+    return g_err;
+}
+}  // namespace dspi
+
 struct dspi_eq {
     dspi_eq_desc desc;
     int cpl;                 // channels per lane (float: 1 or 2; Q28: 1)

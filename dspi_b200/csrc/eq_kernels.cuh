@@ -31,6 +31,9 @@ struct EqLaunch {
     uint32_t dbg;          // diagnostics only (env DSPI_DBG): 1 = skip arithmetic, 2 = skip HBM traffic
 };
 
+// per-thread message buffer behind dspi_last_error() (engine.cu)
+char *error_buffer(size_t *cap);
+
 // K1 — float cascade.  cpl: channels per lane (1 scalar FFMA, 2 packed FFMA2)
 cudaError_t launch_eq_f32(const EqLaunch &a, bool fused, int cpl, cudaStream_t stream);
 cudaError_t launch_pack_f32(const dspi_biquad_f32 *aos, uint32_t ch0, uint32_t n, float *coef, uint64_t *modes, int cpl, cudaStream_t stream);

@@ -85,3 +85,21 @@ assert CROSSPOINT.itemsize == 12 and OUTPUT.itemsize == 20
 assert XFEED_F32.itemsize == 28 and LEV_COEFFS.itemsize == 36
 assert LEV_STATE_F32.itemsize == 3864 and LEV_STATE_Q28.itemsize == 3864
 assert LOUD_F32.itemsize == 28 and LOUD_Q28.itemsize == 24 and PDM_STATE.itemsize == 36
+
+# ---- full-chain records (include/dspi_b200.h) ---------------------------------------------------
+CHAIN_OUTPUTS = 9
+CHAIN_EQ_CHANNELS = 11
+CHAIN_MAX_DELAY = 4096
+
+# config.h:403-406 — MatrixMixer, RP2350 (396 bytes)
+MATRIX_MIXER_F32 = np.dtype([("crosspoints", CROSSPOINT, (2, CHAIN_OUTPUTS)), ("outputs", OUTPUT, (CHAIN_OUTPUTS,))])
+# config.h:455-460 — SystemStatusPacket, RP2350 (26 bytes)
+STATUS = np.dtype([("peaks", np.uint16, (CHAIN_EQ_CHANNELS,)), ("cpu0_load", _b), ("cpu1_load", _b), ("clip_flags", np.uint16)])
+# dspi_chain_params_f32 (544 bytes)
+CHAIN_PARAMS_F32 = np.dtype({
+    "names": ["bypass_master_eq", "loudness_enabled", "crossfeed_enabled", "leveller_enabled", "host_mute", "leveller_lookahead",
+              "host_vol_mul", "preset_mute_gain", "master_volume_linear", "preamp_linear", "loudness", "crossfeed", "leveller", "matrix"],
+    "formats": [_b, _b, _b, _b, _b, _b, np.int16, _f, _f, (_f, (2,)), (LOUD_F32, (2,)), XFEED_F32, LEV_COEFFS, MATRIX_MIXER_F32],
+    "offsets": [0, 1, 2, 3, 4, 5, 8, 12, 16, 20, 28, 84, 112, 148],
+    "itemsize": 544})
+assert MATRIX_MIXER_F32.itemsize == 396 and STATUS.itemsize == 26 and CHAIN_PARAMS_F32.itemsize == 544

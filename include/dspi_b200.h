@@ -145,6 +145,102 @@ void *dspi_eq_stream(dspi_eq *e);
 /* number of kernel launches issued by this engine so far */
 uint64_t dspi_eq_launch_count(dspi_eq *e);
 
+/* ---- full signal chain: many independent DSPi device instances ------------------------------ */
+/* One instance = process_audio_packet() of one RP2350-shape device (usb_audio.c:500-1317, float
+ * pipeline :560-967, single-core branch :874-960): 2 inputs -> preamp -> loudness -> master EQ ->
+ * leveller -> crossfeed -> 2x9 matrix -> per-output EQ, gain, delay -> 4 S/PDIF stereo pairs
+ * (24-bit words) + the PDM sub through the 2nd-order delta-sigma modulator (pdm_generator.c:351-397). */
+#define DSPI_CHAIN_OUTPUTS      9    /* config.h:321 NUM_OUTPUT_CHANNELS                            */
+#define DSPI_CHAIN_EQ_CHANNELS 11    /* config.h:322 NUM_CHANNELS: master L, R, Out1..9             */
+#define DSPI_CHAIN_MAX_DELAY 4096    /* config.h:84  MAX_DELAY_SAMPLES                              */
+
+/* LoudnessCoeffs (RP2350), loudness.h:11-17 (28 bytes) */
+typedef struct { float sva1, sva2, sva3, svm0, svm1, svm2; uint8_t bypass; } dspi_loudness_coeffs_f32;
+/* CrossfeedState (RP2350), crossfeed.h:46-51 (28 bytes) */
+typedef struct { float lp_a0, lp_b1, lp_state_L, lp_state_R, ap_a, ap_state_L, ap_state_R; } dspi_crossfeed_state_f32;
+/* LevellerCoeffs, leveller.h:81-99 (36 bytes) */
+typedef struct {
+    float alpha_rms, alpha_attack, alpha_release;
+    float threshold_db, ratio, knee_width_db, makeup_db, gate_threshold_db, max_gain_db;
+} dspi_leveller_coeffs;
+/* MatrixCrosspoint / OutputChannel / MatrixMixer, config.h:383-406 (12 / 20 / 396 bytes) */
+typedef struct __attribute__((packed)) { uint8_t enabled, phase_invert, reserved[2]; float gain_db, gain_linear; } dspi_matrix_crosspoint;
+typedef struct __attribute__((packed)) { uint8_t enabled, mute, reserved[2]; float gain_db, gain_linear, delay_ms; int32_t delay_samples; } dspi_output_channel;
+typedef struct {
+    dspi_matrix_crosspoint crosspoints[2][DSPI_CHAIN_OUTPUTS];
+    dspi_output_channel outputs[DSPI_CHAIN_OUTPUTS];
+} dspi_matrix_mixer_f32;
+/* SystemStatusPacket, config.h:455-460 (26 bytes): peaks are Q15, clip_flags sticky */
+typedef struct { uint16_t peaks[DSPI_CHAIN_EQ_CHANNELS]; uint8_t cpu0_load, cpu1_load; uint16_t clip_flags; } dspi_status;
+
+/* Everything process_audio_packet() reads besides filters[][]: the globals of usb_audio.c:148-211
+ * for one instance, with the coefficient records in the reference's own layouts. */
+typedef struct {
+    uint8_t bypass_master_eq;        /* usb_audio.c:48                                             */
+    uint8_t loudness_enabled;        /* loud_on && current_loudness_coeffs != NULL, :579-580        */
+    uint8_t crossfeed_enabled;       /* !crossfeed_bypassed                                         */
+    uint8_t leveller_enabled;        /* !leveller_bypassed                                          */
+    uint8_t host_mute;               /* audio_state.mute                                            */
+    uint8_t leveller_lookahead;      /* leveller_config.lookahead                                   */
+    uint8_t reserved0[2];
+    int16_t host_vol_mul;            /* audio_state.vol_mul - an int16: 0 dB gives -32768 (quirk)   */
+    int16_t reserved1;
+    float preset_mute_gain;          /* update_preset_mute_envelope(), 1.0 when no preset loads     */
+    float master_volume_linear;      /* usb_audio.c:161                                             */
+    float preamp_linear[2];          /* global_preamp_linear[]                                      */
+    dspi_loudness_coeffs_f32 loudness[2];   /* the selected row of loudness_active_table            */
+    dspi_crossfeed_state_f32 crossfeed;     /* coefficients AND state (crossfeed_compute_coefficients clears state) */
+    dspi_leveller_coeffs leveller;
+    dspi_matrix_mixer_f32 matrix;    /* outputs[o].delay_samples is channel_delay_samples[o]        */
+} dspi_chain_params_f32;
+
+#ifdef __cplusplus
+static_assert(sizeof(dspi_loudness_coeffs_f32) == 28 && sizeof(dspi_crossfeed_state_f32) == 28 && sizeof(dspi_leveller_coeffs) == 36 &&
+              sizeof(dspi_matrix_mixer_f32) == 396 && sizeof(dspi_status) == 26, "reference layouts");
+#else
+_Static_assert(sizeof(dspi_loudness_coeffs_f32) == 28 && sizeof(dspi_crossfeed_state_f32) == 28 && sizeof(dspi_leveller_coeffs) == 36 &&
+               sizeof(dspi_matrix_mixer_f32) == 396 && sizeof(dspi_status) == 26, "reference layouts");
+#endif
+
+typedef struct dspi_chain dspi_chain;
+typedef struct {
+    uint32_t arith;          /* DSPI_ARITH_F32_FUSED or DSPI_ARITH_F32_STRICT                       */
+    uint32_t n_instances;
+    uint32_t n_bands;        /* channel_band_counts[] value (10)                                    */
+    int32_t  device;
+    uint32_t max_frames;     /* largest n_packets * frames_per_packet of one process call           */
+} dspi_chain_desc;
+
+int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc);
+int dspi_chain_destroy(dspi_chain *c);
+/* bulk_params_apply()-style update between packets (bulk_params.c:178-377 + main.c:1126-1162):
+ * params[n] for instances [inst0, inst0+n).  Filter, delay-line, leveller and PDM state are kept. */
+int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_chain_params_f32 *params);
+/* filters[NUM_CHANNELS][MAX_BANDS] of n instances: biquads[n][11][12] (master L, R, Out1..9) */
+int dspi_chain_upload_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_biquad_f32 *biquads);
+int dspi_chain_download_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, dspi_biquad_f32 *biquads);
+/* pipeline reset: clears leveller, loudness, delay-line and PDM state (leveller_reset_state(),
+ * pdm_processing_loop() restart path); filter state is part of the biquads */
+int dspi_chain_reset_state(dspi_chain *c);
+/* n_packets USB packets of frames_per_packet (<= 192) frames for every instance.
+ *   pcm:       [n_instances][n_packets * frames_per_packet] interleaved L,R little-endian frames,
+ *              bit_depth 16 (4 bytes / frame) or 24 (packed, 6 bytes / frame)      (HOST memory)
+ *   spdif_out: [n_instances][4][n_frames][2] int32 - the four pico_audio producer buffers
+ *   pdm_out:   [n_instances][n_frames][8] uint32 - 256 PDM bits per frame, MSB first (written only
+ *              for instances whose sub output is enabled)
+ *   status:    [n_instances], peaks of the LAST packet, clip flags OR-ed in (sticky)
+ * Any of the three outputs may be NULL. */
+int dspi_chain_process_host(dspi_chain *c, const void *pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t frames_per_packet,
+                            int32_t *spdif_out, uint32_t *pdm_out, dspi_status *status);
+/* same with DEVICE pointers; asynchronous on the engine stream */
+int dspi_chain_process_device(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t frames_per_packet,
+                              int32_t *d_spdif_out, uint32_t *d_pdm_out, dspi_status *d_status);
+int dspi_chain_sync(dspi_chain *c);
+void *dspi_chain_stream(dspi_chain *c);
+uint64_t dspi_chain_launch_count(dspi_chain *c);
+/* dsp_update_delay_samples() for one output, dsp_pipeline.c:216-239 (is_last adds SUB_ALIGN_SAMPLES) */
+int32_t dspi_delay_samples(float delay_ms, float sample_rate, int is_last);
+
 /* pinned host memory helpers */
 void *dspi_host_alloc(size_t bytes);
 void dspi_host_free(void *p);

@@ -1,0 +1,88 @@
+"""Seeded configurations for the whole-chain parity tests (BASELINE config 3 shape, shrunk)."""
+import ctypes as C
+
+import numpy as np
+
+from dspi_b200 import api, layouts as L, workloads as W
+
+
+def chain_params(oracle, N, fs, seed, leveller=True, uniform=False):
+    """CHAIN_PARAMS_F32 [N] + biquads [N, 11, 12]: every stage exercised, per-instance variety."""
+    rng = np.random.default_rng(seed)
+    P = np.zeros(N, L.CHAIN_PARAMS_F32)
+    loud_tab = np.zeros((L.LOUD_STEPS, 2), L.LOUD_F32)
+    oracle.lib.orc_loud_table_f32(loud_tab.ctypes.data, 83.0, 100.0, fs)
+    for i in range(N):
+        p = P[i]
+        u = rng.random(16)
+        vol_8_8 = int(-40 * 256 * u[0])                       # host volume 0 .. -40 dB
+        idx = C.c_uint8()
+        p["host_vol_mul"] = oracle.lib.orc_host_vol_mul(vol_8_8, C.byref(idx))
+        p["host_mute"] = 1 if (not uniform and u[1] < 0.05) else 0
+        p["preset_mute_gain"] = 1.0
+        p["master_volume_linear"] = np.float32(10.0 ** (-6.0 * u[2] / 20.0))
+        p["preamp_linear"] = [np.float32(10.0 ** ((-3 + 6 * u[3]) / 20.0)), np.float32(10.0 ** ((-3 + 6 * u[4]) / 20.0))]
+        p["bypass_master_eq"] = 1 if (not uniform and u[5] < 0.15) else 0
+        p["loudness_enabled"] = 1 if (uniform or u[6] < 0.7) else 0
+        p["loudness"] = loud_tab[idx.value]
+        xcfg = (C.c_uint8 * 12)()
+        xn = np.frombuffer(xcfg, np.uint8)
+        xn[0], xn[1], xn[2] = 1, (1 if u[7] < 0.8 else 0), int(u[8] * 4) % 4
+        xn[4:8] = np.frombuffer(np.float32(500 + 1500 * u[9]).tobytes(), np.uint8)
+        xn[8:12] = np.frombuffer(np.float32(15 * u[10]).tobytes(), np.uint8)
+        xst = np.zeros(1, L.XFEED_F32)
+        oracle.lib.orc_xfeed_coeffs_f32(xst.ctypes.data, C.addressof(xcfg), fs)
+        p["crossfeed"] = xst[0]
+        p["crossfeed_enabled"] = 1 if (uniform or u[11] < 0.7) else 0
+        lcfg = np.zeros(24, np.uint8)
+        lcfg[0] = 1
+        lcfg[4:8] = np.frombuffer(np.float32(100 * u[12]).tobytes(), np.uint8)
+        lcfg[8] = int(u[13] * 3) % 3
+        lcfg[12:16] = np.frombuffer(np.float32(15.0).tobytes(), np.uint8)
+        lcfg[16] = 1
+        lcfg[20:24] = np.frombuffer(np.float32(-96.0).tobytes(), np.uint8)
+        lc = np.zeros(1, L.LEV_COEFFS)
+        oracle.lib.orc_lev_coeffs_compute(lc.ctypes.data, lcfg.ctypes.data, fs)
+        p["leveller"] = lc[0]
+        p["leveller_enabled"] = 1 if (leveller and (uniform or u[14] < 0.6)) else 0
+        p["leveller_lookahead"] = 1 if (uniform or u[15] < 0.5) else 0
+        m = p["matrix"]
+        v = rng.random((9, 8))
+        for o in range(9):
+            oc = m["outputs"][o]
+            oc["enabled"] = 1 if (uniform or v[o, 0] < 0.85) else 0
+            oc["mute"] = 1 if (not uniform and v[o, 1] < 0.1) else 0
+            oc["gain_db"] = np.float32(-6 * v[o, 2])
+            oc["gain_linear"] = np.float32(10.0 ** (float(oc["gain_db"]) / 20.0))
+            oc["delay_ms"] = np.float32(40.0 * v[o, 3]) if v[o, 4] < 0.7 else np.float32(0.0)
+            oc["delay_samples"] = api.delay_samples(float(oc["delay_ms"]), fs, o == 8)
+            # L -> odd outputs, R -> even, (L+R)/2 -> sub, plus some random routes and inversions
+            for side in range(2):
+                x = m["crosspoints"][side, o]
+                on = (o == 8) or (o % 2 == side) or (not uniform and v[o, 5 + side] < 0.2)
+                x["enabled"] = 1 if on else 0
+                x["phase_invert"] = 1 if (not uniform and v[o, 7] < 0.2 and side == 1) else 0
+                x["gain_db"] = np.float32(-6.0 if o == 8 else 0.0)
+                x["gain_linear"] = np.float32(0.5 if o == 8 else 1.0)
+    # EQ recipes: per role; per instance variety unless `uniform`
+    bq = np.zeros((N, L.CHAIN_EQ_CHANNELS, L.MAX_BANDS), L.BIQUAD_F32)
+    for i in range(N):
+        variant = "B" if uniform else ("mixed" if i % 3 == 0 else ("A" if i % 3 == 1 else "B"))
+        params = W.eq_params(variant, L.CHAIN_EQ_CHANNELS, fs=fs, seed=seed + (0 if uniform else i))
+        bq[i] = api.compute_coefficients(params, q28=False, fs=fs)
+        if not uniform and i % 7 == 3:
+            bq[i, 4]["bypass"] = 1            # a fully flat output EQ (channel_bypassed)
+    return P, bq
+
+
+def pcm_bytes(N, F, bit_depth, seed):
+    rng = np.random.default_rng(seed)
+    if bit_depth == 16:
+        s = (rng.integers(-20000, 20000, (N, F, 2))).astype("<i2")
+        return s.view(np.uint8).reshape(N, F * 4)
+    s = rng.integers(-(1 << 22), 1 << 22, (N, F, 2)).astype(np.int32)
+    b = np.zeros((N, F, 2, 3), np.uint8)
+    b[..., 0] = s & 0xFF
+    b[..., 1] = (s >> 8) & 0xFF
+    b[..., 2] = (s >> 16) & 0xFF
+    return b.reshape(N, F * 6)

@@ -172,3 +172,115 @@ class Ref:
 
     def leveller(self, st, coeffs, lookahead, l, r):
         self.lib.ref_leveller(_ptr(st), _ptr(coeffs), int(lookahead), _ptr(l), _ptr(r), l.shape[0])
+
+
+# ---- whole-instance records of the oracle (oracle/dspi_oracle.h) -----------------------------
+class OrcCrosspoint(C.Structure):
+    _pack_ = 1
+    _fields_ = [("enabled", C.c_uint8), ("phase_invert", C.c_uint8), ("reserved", C.c_uint8 * 2),
+                ("gain_db", C.c_float), ("gain_linear", C.c_float)]
+
+
+class OrcOutput(C.Structure):
+    _pack_ = 1
+    _fields_ = [("enabled", C.c_uint8), ("mute", C.c_uint8), ("reserved", C.c_uint8 * 2), ("gain_db", C.c_float),
+                ("gain_linear", C.c_float), ("delay_ms", C.c_float), ("delay_samples", C.c_int32)]
+
+
+class OrcBiquadF32(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("b0", "b1", "b2", "a1", "a2", "s1", "s2", "sva1", "sva2", "sva3", "svm0", "svm1", "svm2",
+                                         "svic1eq", "svic2eq")] + [("svf_type", C.c_uint32), ("use_svf", C.c_uint8), ("bypass", C.c_uint8)]
+
+
+class OrcLoudF32(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("sva1", "sva2", "sva3", "svm0", "svm1", "svm2")] + [("bypass", C.c_uint8)]
+
+
+class OrcSvfState(C.Structure):
+    _fields_ = [("ic1eq", C.c_float), ("ic2eq", C.c_float)]
+
+
+class OrcXfeedF32(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("lp_a0", "lp_b1", "lp_state_L", "lp_state_R", "ap_a", "ap_state_L", "ap_state_R")]
+
+
+class OrcLevCoeffs(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("alpha_rms", "alpha_attack", "alpha_release", "threshold_db", "ratio", "knee_width_db",
+                                         "makeup_db", "gate_threshold_db", "max_gain_db")]
+
+
+class OrcLevStateF32(C.Structure):
+    _fields_ = [("env_sq_l", C.c_float), ("env_sq_r", C.c_float), ("gain_smooth_db", C.c_float), ("gain_linear", C.c_float),
+                ("gain_prev_linear", C.c_float), ("lookahead_buf", (C.c_float * 480) * 2), ("la_write_idx", C.c_uint32)]
+
+
+class OrcPdm(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("err1", "err2", "x1", "x2", "y1", "y2", "err_acc")] + [("rng", C.c_uint32), ("fade_in_pos", C.c_uint32)]
+
+
+class OrcChainF32(C.Structure):
+    _fields_ = [("n_out", C.c_uint32), ("n_bands", C.c_uint32), ("max_delay", C.c_uint32),
+                ("bypass_master_eq", C.c_uint8), ("loudness_on", C.c_uint8), ("crossfeed_on", C.c_uint8), ("leveller_on", C.c_uint8),
+                ("host_mute", C.c_uint8), ("any_delay_active", C.c_uint8), ("lev_lookahead", C.c_uint8), ("pad0", C.c_uint8),
+                ("host_vol_mul", C.c_int16), ("pad1", C.c_int16), ("preset_mute_gain", C.c_float), ("master_volume_linear", C.c_float),
+                ("preamp_linear", C.c_float * 2), ("xp", (OrcCrosspoint * 9) * 2), ("out", OrcOutput * 9), ("delay_samples", C.c_int32 * 9),
+                ("channel_bypassed", C.c_uint8 * 11), ("pad2", C.c_uint8), ("filters", (OrcBiquadF32 * 12) * 11), ("loud", OrcLoudF32 * 2),
+                ("loud_state", (OrcSvfState * 2) * 2), ("xfeed", OrcXfeedF32), ("levc", OrcLevCoeffs), ("levs", OrcLevStateF32),
+                ("delay_lines", (C.c_float * 4096) * 9), ("delay_widx", C.c_uint32), ("pdm", OrcPdm), ("peaks", C.c_uint16 * 11),
+                ("clip_flags", C.c_uint16)]
+
+
+def make_orc_chain(oracle, params, biquads):
+    """orc_chain_f32 for one instance from a CHAIN_PARAMS_F32 record and its [11, 12] biquads."""
+    assert C.sizeof(OrcChainF32) == oracle.lib.orc_sizeof(2)
+    c = OrcChainF32()
+    c.n_out, c.n_bands, c.max_delay = 9, 10, 4096
+    c.bypass_master_eq = int(params["bypass_master_eq"])
+    c.loudness_on = int(params["loudness_enabled"])
+    c.crossfeed_on = int(params["crossfeed_enabled"])
+    c.leveller_on = int(params["leveller_enabled"])
+    c.host_mute = int(params["host_mute"])
+    c.lev_lookahead = int(params["leveller_lookahead"])
+    c.host_vol_mul = int(params["host_vol_mul"])
+    c.preset_mute_gain = float(params["preset_mute_gain"])
+    c.master_volume_linear = float(params["master_volume_linear"])
+    c.preamp_linear[0], c.preamp_linear[1] = float(params["preamp_linear"][0]), float(params["preamp_linear"][1])
+    m = params["matrix"]
+    any_delay = False
+    for o in range(9):
+        for i in range(2):
+            x = m["crosspoints"][i, o]
+            c.xp[i][o].enabled, c.xp[i][o].phase_invert = int(x["enabled"]), int(x["phase_invert"])
+            c.xp[i][o].gain_db, c.xp[i][o].gain_linear = float(x["gain_db"]), float(x["gain_linear"])
+        oc = m["outputs"][o]
+        c.out[o].enabled, c.out[o].mute = int(oc["enabled"]), int(oc["mute"])
+        c.out[o].gain_db, c.out[o].gain_linear = float(oc["gain_db"]), float(oc["gain_linear"])
+        c.out[o].delay_ms, c.out[o].delay_samples = float(oc["delay_ms"]), int(oc["delay_samples"])
+        c.delay_samples[o] = int(oc["delay_samples"])
+        any_delay = any_delay or int(oc["delay_samples"]) > 0
+    c.any_delay_active = 1 if any_delay else 0
+    C.memmove(C.addressof(c.filters), np.ascontiguousarray(biquads).ctypes.data, 11 * 12 * 68)
+    for r in range(11):
+        c.channel_bypassed[r] = 1 if all(int(biquads[r, b]["bypass"]) for b in range(10)) else 0
+    for j in range(2):
+        C.memmove(C.addressof(c.loud[j]), params["loudness"][j:j + 1].tobytes(), 28)
+    C.memmove(C.addressof(c.xfeed), params["crossfeed"].tobytes(), 28)
+    C.memmove(C.addressof(c.levc), params["leveller"].tobytes(), 36)
+    c.levs.gain_linear = 1.0
+    c.levs.gain_prev_linear = 1.0
+    c.pdm.rng = 123456789
+    return c
+
+
+def orc_chain_run(oracle, flavour, chain, pcm_bytes, bit_depth, n_packets, fpp):
+    """Runs n_packets packets through one oracle instance; returns (spdif [4, F, 2], pdm [F, 8])."""
+    F = n_packets * fpp
+    bpf = 6 if bit_depth == 24 else 4
+    spdif = np.zeros((4, F, 2), np.int32)
+    pdm = np.zeros((F, 8), np.uint32)
+    fn = getattr(oracle.lib, f"orc_{flavour}_chain_packet")
+    data = np.ascontiguousarray(pcm_bytes)
+    for p in range(n_packets):
+        fn(C.addressof(chain), data.ctypes.data + p * fpp * bpf, fpp * bpf, bit_depth,
+           spdif.ctypes.data + p * fpp * 8, F * 2, pdm.ctypes.data + p * fpp * 32)
+    return spdif, pdm
