@@ -142,6 +142,77 @@ def cpu_reference_run(variant, arith, frames, target_seconds, steps=1, warmup=0)
     return sps, info, Cn
 
 
+def _time_eq(api, torch, arith, bq, Cn, T, steps=6, q=False):
+    eng = api.EqEngine(arith, Cn)
+    eng.upload(bq)
+    bufs = []
+    for i in range(3):
+        if q:
+            bufs.append(torch.randint(-2**27, 2**27, (Cn, T), dtype=torch.int32, device="cuda"))
+        else:
+            bufs.append(torch.rand((Cn, T), dtype=torch.float32, device="cuda") - 0.5)
+    torch.cuda.synchronize()
+    st = torch.cuda.ExternalStream(eng.stream)
+    for i in range(3):
+        eng.process_device(bufs[i % 3].data_ptr(), T, T)
+    eng.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for i in range(steps):
+        eng.process_device(bufs[i % 3].data_ptr(), T, T)
+    e1.record(st)
+    eng.sync()
+    ms = e0.elapsed_time(e1) / steps
+    eng.close()
+    del bufs
+    torch.cuda.empty_cache()
+    peak, _ = measured_peak_gbs()
+    sps = Cn * T / (ms * 1e-3)
+    return {"samples_per_s": sps, "ms_per_step": ms, "hbm_frac": sps * ALG_BYTES_PER_SAMPLE / 1e9 / peak, "channels": Cn, "frames": T}
+
+
+def extra_configs(api, W, L, torch):
+    """The other BASELINE configs, short runs (device-resident, CUDA events): reported beside the headline."""
+    out = {}
+    T = 6144
+    try:
+        p = W.eq_params_fast("B", CHANNELS_PER_GPU, fs=FS, seed=1)
+        out["cfg2_variantB_f32_fused"] = _time_eq(api, torch, "f32f", api.compute_coefficients(p, fs=FS), CHANNELS_PER_GPU, T)
+        p = W.eq_params_fast("A", CHANNELS_PER_GPU, fs=FS, seed=1)
+        out["cfg2_variantA_f32_strict"] = _time_eq(api, torch, "f32s", api.compute_coefficients(p, fs=FS), CHANNELS_PER_GPU, T)
+        p = W.eq_params_fast("B", 32768, fs=FS, seed=1)
+        out["cfg4_q28_32768ch"] = _time_eq(api, torch, "q28", api.compute_coefficients(p, q28=True, fs=FS), 32768, T, q=True)
+        # config 3: 8192 instances (65536 S/PDIF channels + 8192 PDM subs), s24 packets of 96 frames
+        N, fpp, npk = 8192, 96, 16
+        F = fpp * npk
+        P, bq = W.chain_config3(N, fs=FS, seed=1)
+        eng = api.ChainEngine("f32f", N, max_frames=F)
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        pcm = torch.randint(0, 256, (N, F * 6), dtype=torch.uint8, device="cuda")
+        spdif = torch.empty((N, 4, F, 2), dtype=torch.int32, device="cuda")
+        pdm = torch.empty((N, F, 8), dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        st = torch.cuda.ExternalStream(eng.stream)
+        eng.process_device(pcm.data_ptr(), 24, npk, fpp, spdif.data_ptr(), pdm.data_ptr())
+        eng.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record(st)
+        for _ in range(reps):
+            eng.process_device(pcm.data_ptr(), 24, npk, fpp, spdif.data_ptr(), pdm.data_ptr())
+        e1.record(st)
+        eng.sync()
+        ms = e0.elapsed_time(e1) / reps
+        eng.close()
+        out["cfg3_full_chain_8192inst"] = {"instance_frames_per_s": N * F / (ms * 1e-3), "output_channel_samples_per_s": N * 9 * F / (ms * 1e-3),
+                                           "ms_per_step": ms, "instances": N, "frames": F, "realtime_factor": (F / FS) / (ms * 1e-3),
+                                           "bytes_per_instance_frame": {"pcm_in": 6, "spdif_out": 32, "pdm_out": 32}}
+    except Exception as e:                     # extras must never break the headline line
+        out["error"] = repr(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,6 +225,7 @@ def main():
     ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -189,7 +261,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     q = args.arith == "q28"
     Cn, T = args.channels, args.frames
-    ch0 = rank * Cn                                       # contiguous channel shard of the whole job
+    from dspi_b200 import sharding
+    ch0, _ = sharding.shard_range(Cn * world, rank, world)    # contiguous channel shard of the whole job
 
     params = W.eq_params_fast(args.variant if not q else "B", Cn, fs=FS, seed=1, ch0=ch0)
     bq = api.compute_coefficients(params, q28=q, fs=FS)
@@ -282,6 +355,40 @@ def main():
         _, cpu, _ = cpu_reference_run(args.variant, args.arith, T, target_seconds=10.0)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
+    # ---- N>1: frames originate on rank 0 and travel over NCCL/NVLink (scatter in, gather out) ----
+    nccl = None
+    if world > 1:
+        total = Cn * world
+        full = None
+        if rank == 0:
+            full = torch.rand((total, T), dtype=torch.float32, device="cuda") - 0.5 if not q else \
+                torch.randint(-2**27, 2**27, (total, T), dtype=torch.int32, device="cuda")
+        dt_t = torch.int32 if q else torch.float32
+        def sg_step():
+            mine = sharding.scatter_rows(full, total, T, dt_t, "cuda")
+            torch.cuda.current_stream().synchronize()
+            eng.process_device(mine.data_ptr(), T, T)
+            eng.sync()
+            return sharding.gather_rows(mine, total)
+        sg_step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_sg = 3
+        for _ in range(n_sg):
+            sg_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        nccl = {"value": float(total) * T * n_sg / float(dt.item()), "unit": "samples/s", "steps": n_sg,
+                "path": "rank 0 holds all frames: isend/irecv scatter over NCCL -> per-rank kernel -> gather to rank 0",
+                "bytes_over_nvlink_per_step": int(total - Cn) * T * 4 * 2}
+        del full
+
+    other = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        other = extra_configs(api, W, L, torch)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -290,6 +397,7 @@ def main():
                            "arith": args.arith, "variant": args.variant, "parallelism": f"channel-sharded dp{world}, no collective on the data path",
                            "l2": f"inputs larger than L2: {nbuf} rotating buffers of {Cn * T * 4 / 2**30:.2f} GiB", "layout": "channel-major [C][T], in place"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "nccl_scatter_gather": nccl, "other_configs": other,
                 "realtime_factor": value / (Cn * world * FS)}
         print(json.dumps(line))
     eng.close()

@@ -25,6 +25,7 @@ SYMBOLS = [
     "dspi_chain_create", "dspi_chain_destroy", "dspi_chain_set_params", "dspi_chain_upload_biquads", "dspi_chain_download_biquads",
     "dspi_chain_reset_state", "dspi_chain_process_host", "dspi_chain_process_device", "dspi_chain_sync", "dspi_chain_stream",
     "dspi_chain_launch_count", "dspi_delay_samples",
+    "dspi_crossfeed_compute_coefficients_f32", "dspi_leveller_compute_coefficients", "dspi_loudness_compute_table_f32", "dspi_host_volume",
 ]
 
 
@@ -85,6 +86,11 @@ def lib():
         h.dspi_chain_launch_count.restype = C.c_uint64
         h.dspi_delay_samples.argtypes = [C.c_float, C.c_float, C.c_int]
         h.dspi_delay_samples.restype = C.c_int32
+        h.dspi_crossfeed_compute_coefficients_f32.argtypes = [vp, vp, C.c_float]
+        h.dspi_leveller_compute_coefficients.argtypes = [vp, vp, C.c_float]
+        h.dspi_loudness_compute_table_f32.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+        h.dspi_host_volume.argtypes = [C.c_int16, vp]
+        h.dspi_host_volume.restype = C.c_int16
         h.dspi_host_alloc.argtypes = [C.c_size_t]
         h.dspi_host_alloc.restype = vp
         h.dspi_host_free.argtypes = [vp]
@@ -268,3 +274,40 @@ class ChainEngine:
 
 def delay_samples(delay_ms, fs, is_last=False):
     return int(lib().dspi_delay_samples(delay_ms, fs, 1 if is_last else 0))
+
+
+class _XfeedCfg(C.Structure):
+    _fields_ = [("enabled", C.c_uint8), ("itd_enabled", C.c_uint8), ("preset", C.c_uint8), ("custom_fc", C.c_float), ("custom_feed_db", C.c_float)]
+
+
+class _LevCfg(C.Structure):
+    _fields_ = [("enabled", C.c_uint8), ("amount", C.c_float), ("speed", C.c_uint8), ("max_gain_db", C.c_float),
+                ("lookahead", C.c_uint8), ("gate_threshold_db", C.c_float)]
+
+
+def crossfeed_coefficients(fs, enabled=True, itd=True, preset=0, custom_fc=700.0, custom_feed_db=4.5):
+    """``crossfeed_compute_coefficients`` -> XFEED_F32 record (state cleared)."""
+    st = np.zeros(1, L.XFEED_F32)
+    cfg = _XfeedCfg(int(enabled), int(itd), int(preset), custom_fc, custom_feed_db)
+    lib().dspi_crossfeed_compute_coefficients_f32(st.ctypes.data, C.byref(cfg), fs)
+    return st[0]
+
+
+def leveller_coefficients(fs, amount=50.0, speed=0, max_gain_db=15.0, gate_db=-96.0):
+    out = np.zeros(1, L.LEV_COEFFS)
+    cfg = _LevCfg(1, amount, int(speed), max_gain_db, 1, gate_db)
+    lib().dspi_leveller_compute_coefficients(out.ctypes.data, C.byref(cfg), fs)
+    return out[0]
+
+
+def loudness_table(fs, ref_spl=83.0, intensity_pct=100.0):
+    t = np.zeros((L.LOUD_STEPS, 2), L.LOUD_F32)
+    lib().dspi_loudness_compute_table_f32(t.ctypes.data, ref_spl, intensity_pct, fs)
+    return t
+
+
+def host_volume(volume_8_8):
+    """``audio_set_volume``: returns (vol_mul as int16, loudness table row)."""
+    idx = C.c_uint8()
+    v = lib().dspi_host_volume(int(volume_8_8), C.byref(idx))
+    return int(v), int(idx.value)

@@ -171,3 +171,151 @@ void dspi_compute_coefficients_q28(dspi_eq_param *p, dspi_biquad_q28 *bq, float 
     bq->a1 = to_q28(d[1] / d[0]);
     bq->a2 = to_q28(d[2] / d[0]);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Crossfeed, leveller, loudness and host-volume parameter functions (float / RP2350 stores).
+ * Same role as crossfeed_compute_coefficients() (crossfeed.c:35-127),
+ * leveller_compute_coefficients() (leveller.c:42-89), loudness_recompute_table()
+ * (loudness.c:169-217) and audio_set_volume() (usb_audio.c:410-440).
+ * ---------------------------------------------------------------------------------------------- */
+
+void dspi_crossfeed_compute_coefficients_f32(dspi_crossfeed_state_f32 *st, const dspi_crossfeed_config *cfg, float fs)
+{
+    static const float preset_fc[3] = { 700.0f, 700.0f, 650.0f };          /* crossfeed.c:25-29 */
+    static const float preset_db[3] = { 4.5f, 6.0f, 9.5f };
+    memset(st, 0, sizeof(*st));                                             /* disabled: crossfeed_init() */
+    if (!cfg->enabled || fs < 1.0f) return;
+    float fc, feed_db;
+    if (cfg->preset < 3) {
+        fc = preset_fc[cfg->preset];
+        feed_db = preset_db[cfg->preset];
+    } else {                                                                /* :47-52 custom, clamped */
+        fc = cfg->custom_fc;
+        feed_db = cfg->custom_feed_db;
+        if (fc < 500.0f) fc = 500.0f;
+        if (fc > 2000.0f) fc = 2000.0f;
+        if (feed_db < 0.0f) feed_db = 0.0f;
+        if (feed_db > 15.0f) feed_db = 15.0f;
+    }
+    const float level_ratio = powf(10.0f, feed_db / 20.0f);                 /* :67-68 */
+    const float G = 1.0f / (1.0f + level_ratio);
+    const float x = expf(-2.0f * PI_F * fc / fs);                           /* :75-77 */
+    st->lp_a0 = G * (1.0f - x);
+    st->lp_b1 = x;
+    float ap = 1.0f;                                                        /* :97-109 */
+    if (cfg->itd_enabled) {
+        const float lp_delay_sec = x / ((1.0f - x) * fs);
+        const float remaining_sec = 0.000220f - lp_delay_sec;
+        if (remaining_sec > 0.0f) {
+            const float D = remaining_sec * fs;
+            ap = (1.0f - D) / (1.0f + D);
+        }
+    }
+    st->ap_a = ap;
+}
+
+static float retention(float fs, float seconds)                             /* leveller.c:37-40 */
+{
+    if (seconds <= 0.0f || fs <= 0.0f) return 0.0f;
+    return expf(-logf(10.0f) / (fs * seconds));
+}
+
+void dspi_leveller_compute_coefficients(dspi_leveller_coeffs *out, const dspi_leveller_config *cfg, float fs)
+{
+    /* {attack, release, rms window} seconds per speed preset, leveller.c:23-27 */
+    static const float presets[3][3] = { { 0.100f, 2.000f, 0.400f }, { 0.050f, 1.000f, 0.200f }, { 0.020f, 0.500f, 0.100f } };
+    if (fs < 1.0f) fs = 48000.0f;
+    const unsigned spd = cfg->speed >= 3 ? 1u : cfg->speed;
+    out->alpha_rms = retention(fs, presets[spd][2]);
+    out->alpha_attack = retention(fs, presets[spd][0]);
+    out->alpha_release = retention(fs, presets[spd][1]);
+    out->threshold_db = -20.0f;                                             /* leveller.h:51-52 */
+    out->knee_width_db = 6.0f;
+    float gate = cfg->gate_threshold_db;
+    if (gate < -96.0f) gate = -96.0f;
+    if (gate > 0.0f) gate = 0.0f;
+    out->gate_threshold_db = gate;
+    float amount = cfg->amount;
+    if (amount < 0.0f) amount = 0.0f;
+    if (amount > 100.0f) amount = 100.0f;
+    out->ratio = 1.0f + (amount / 100.0f) * 19.0f;                          /* :76-77 */
+    float max_g = cfg->max_gain_db;
+    if (max_g < 0.0f) max_g = 0.0f;
+    if (max_g > 35.0f) max_g = 35.0f;
+    out->max_gain_db = max_g;
+    out->makeup_db = 0.0f;
+}
+
+/* ISO 226:2003 equal-loudness SPL at one tabulated frequency, loudness.c:37-50 */
+static float iso226(float Tf, float af, float Lu, float phon)
+{
+    const float B = 0.4f * powf(10.0f, (Tf + Lu) / 10.0f - 9.0f);
+    float Af = 4.47e-3f * (powf(10.0f, 0.025f * phon) - 1.15f) + powf(B, af);
+    if (Af < 1e-10f) Af = 1e-10f;
+    return (10.0f / af) * log10f(Af) - Lu + 94.0f;
+}
+
+static float shelf_gain_db(float Tf, float af, float Lu, float ref_spl, float phon, float intensity_pct)   /* loudness.c:54-78 */
+{
+    if (phon >= ref_spl) return 0.0f;
+    const float at_ref = iso226(Tf, af, Lu, ref_spl);
+    const float at_eff = iso226(Tf, af, Lu, phon);
+    const float flat_change = phon - ref_spl;
+    const float freq_change = at_eff - at_ref;
+    float comp = freq_change - flat_change;
+    comp *= (intensity_pct / 100.0f);
+    return comp;
+}
+
+static void shelf_svf(float freq, float Q, float gain_db, int high, float fs, dspi_loudness_coeffs_f32 *o)  /* loudness.c:85-130 */
+{
+    if (fabsf(gain_db) < 0.01f) {
+        memset(o, 0, sizeof(*o));
+        o->bypass = 1;
+        return;
+    }
+    o->bypass = 0;
+    const float A = powf(10.0f, gain_db / 40.0f);
+    float g = tanf(PI_F * freq / fs);
+    const float rootA = sqrtf(A);
+    g = high ? g * rootA : g / rootA;
+    const float k = 1.0f / Q;
+    o->sva1 = 1.0f / (1.0f + g * (g + k));
+    o->sva2 = g * o->sva1;
+    o->sva3 = g * o->sva2;
+    if (high) { o->svm0 = A * A; o->svm1 = k * (1.0f - A) * A; o->svm2 = 1.0f - A * A; }
+    else { o->svm0 = 1.0f; o->svm1 = k * (A - 1.0f); o->svm2 = A * A - 1.0f; }
+}
+
+void dspi_loudness_compute_table_f32(dspi_loudness_coeffs_f32 table[61][2], float ref_spl, float intensity_pct, float fs)
+{
+    if (fs < 1.0f) fs = 48000.0f;
+    if (ref_spl < 40.0f) ref_spl = 40.0f;
+    if (ref_spl > 100.0f) ref_spl = 100.0f;
+    memset(table, 0, sizeof(dspi_loudness_coeffs_f32) * 61 * 2);
+    for (int step = 0; step < 61; step++) {
+        float phon = ref_spl + (float)(step - 60);                          /* :186-191 */
+        if (phon < 20.0f) phon = 20.0f;
+        if (phon > ref_spl) phon = ref_spl;
+        const float low_db = shelf_gain_db(44.0f, 0.432f, 80.4f, ref_spl, phon, intensity_pct);    /* 50 Hz row of ISO 226 Table 1 */
+        const float high_db = shelf_gain_db(13.9f, 0.301f, 17.8f, ref_spl, phon, intensity_pct);   /* 10 kHz row */
+        shelf_svf(200.0f, 0.707f, low_db, 0, fs, &table[step][0]);
+        shelf_svf(6000.0f, 0.707f, high_db, 1, fs, &table[step][1]);
+    }
+}
+
+int16_t dspi_host_volume(int16_t volume_8_8, uint8_t *table_index)
+{
+    /* the UAC1 volume table of the firmware, usb_audio.c:410-420 (61 Q15 steps, -60 .. 0 dB) */
+    static const uint16_t q15[61] = {
+        0x0000, 0x0025, 0x0029, 0x002e, 0x0034, 0x003a, 0x0041, 0x0049, 0x0052, 0x005c, 0x0068, 0x0074, 0x0082, 0x0092, 0x00a4, 0x00b8,
+        0x00cf, 0x00e8, 0x0104, 0x0124, 0x0148, 0x0170, 0x019d, 0x01cf, 0x0207, 0x0247, 0x028e, 0x02de, 0x0337, 0x039c, 0x040c, 0x048b,
+        0x0519, 0x05b8, 0x066a, 0x0733, 0x0814, 0x0910, 0x0a2b, 0x0b68, 0x0ccd, 0x0e5d, 0x101d, 0x1215, 0x1449, 0x16c3, 0x198a, 0x1ca8,
+        0x2027, 0x2413, 0x287a, 0x2d6b, 0x32f5, 0x392d, 0x4027, 0x47fb, 0x50c3, 0x5a9e, 0x65ad, 0x7215, 0x8000 };
+    int16_t v = (int16_t)(volume_8_8 + 60 * 256);                           /* :430-432 */
+    if (v < 0) v = 0;
+    if (v >= 61 * 256) v = 61 * 256 - 1;
+    const uint8_t idx = (uint8_t)(((uint16_t)v) >> 8);
+    if (table_index) *table_index = idx;
+    return (int16_t)q15[idx];                                               /* stored in an int16_t: 0 dB -> -32768 */
+}

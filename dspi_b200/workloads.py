@@ -117,3 +117,43 @@ def eq_params_fast(variant, C, fs=96000.0, nbands=L.NUM_BANDS, seed=1, ch0=0):
     else:
         raise ValueError(variant)
     return p
+
+
+def chain_config3(N, fs=96000.0, seed=1, distinct=64):
+    """BASELINE config 3: N RP2350-shape instances, every stage on.
+
+    Matrix L -> Out1/3/5/7, R -> Out2/4/6/8, (L+R)*0.5 -> sub; crossfeed preset 0 with ITD; loudness on
+    at -20 dB host volume; leveller on (slow, look-ahead); output delays uniform in 0-40 ms; all 11 EQ
+    rows with 10 active bands (variant B).  `distinct` different instance configurations are
+    generated with the product's own host parameter API and tiled over the N instances.
+    Returns (CHAIN_PARAMS_F32 [N], BIQUAD_F32 [N, 11, 12]).
+    """
+    from . import api
+    rng = np.random.default_rng(seed)
+    D = min(distinct, N)
+    P = np.zeros(D, L.CHAIN_PARAMS_F32)
+    vol_mul, row = api.host_volume(-20 * 256)
+    table = api.loudness_table(fs, 83.0, 100.0)
+    xf = api.crossfeed_coefficients(fs, True, True, 0)
+    lev = api.leveller_coefficients(fs, 50.0, 0, 15.0, -96.0)
+    bq = np.zeros((D, L.CHAIN_EQ_CHANNELS, L.MAX_BANDS), L.BIQUAD_F32)
+    for i in range(D):
+        p = P[i]
+        p["host_vol_mul"], p["preset_mute_gain"], p["master_volume_linear"] = vol_mul, 1.0, 1.0
+        p["preamp_linear"] = [1.0, 1.0]
+        p["loudness_enabled"], p["crossfeed_enabled"], p["leveller_enabled"], p["leveller_lookahead"] = 1, 1, 1, 1
+        p["loudness"], p["crossfeed"], p["leveller"] = table[row], xf, lev
+        m = p["matrix"]
+        for o in range(L.CHAIN_OUTPUTS):
+            oc = m["outputs"][o]
+            oc["enabled"], oc["mute"], oc["gain_db"], oc["gain_linear"] = 1, 0, 0.0, 1.0
+            oc["delay_ms"] = np.float32(40.0 * rng.random())
+            oc["delay_samples"] = api.delay_samples(float(oc["delay_ms"]), fs, o == L.CHAIN_OUTPUTS - 1)
+            for side in range(2):
+                x = m["crosspoints"][side, o]
+                sub = o == L.CHAIN_OUTPUTS - 1
+                x["enabled"] = 1 if (sub or o % 2 == side) else 0
+                x["gain_db"], x["gain_linear"] = (-6.0206, 0.5) if sub else (0.0, 1.0)
+        bq[i] = api.compute_coefficients(eq_params("B", L.CHAIN_EQ_CHANNELS, fs=fs, seed=seed + i), q28=False, fs=fs)
+    reps = (N + D - 1) // D
+    return np.tile(P, reps)[:N].copy(), np.tile(bq, (reps, 1, 1))[:N].copy()

@@ -202,6 +202,19 @@ _Static_assert(sizeof(dspi_loudness_coeffs_f32) == 28 && sizeof(dspi_crossfeed_s
                sizeof(dspi_matrix_mixer_f32) == 396 && sizeof(dspi_status) == 26, "reference layouts");
 #endif
 
+/* CrossfeedConfig, crossfeed.h:26-32 (12 bytes) and LevellerConfig, leveller.h:59-66 (24 bytes) */
+typedef struct { uint8_t enabled, itd_enabled, preset; float custom_fc, custom_feed_db; } dspi_crossfeed_config;
+typedef struct { uint8_t enabled; float amount; uint8_t speed; float max_gain_db; uint8_t lookahead; float gate_threshold_db; } dspi_leveller_config;
+/* host-side parameter functions of the chain (no GPU needed; host libm, like the firmware's main loop):
+ * crossfeed_compute_coefficients() crossfeed.c:35-127 (clears the filter state),
+ * leveller_compute_coefficients() leveller.c:42-89, loudness_recompute_table() loudness.c:169-217
+ * (table[volume step 0..60][low shelf, high shelf]) and audio_set_volume() usb_audio.c:428-440
+ * (returns audio_state.vol_mul and the loudness table row). */
+void dspi_crossfeed_compute_coefficients_f32(dspi_crossfeed_state_f32 *st, const dspi_crossfeed_config *cfg, float sample_rate);
+void dspi_leveller_compute_coefficients(dspi_leveller_coeffs *out, const dspi_leveller_config *cfg, float sample_rate);
+void dspi_loudness_compute_table_f32(dspi_loudness_coeffs_f32 table[61][2], float ref_spl, float intensity_pct, float sample_rate);
+int16_t dspi_host_volume(int16_t volume_8_8, uint8_t *table_index);
+
 typedef struct dspi_chain dspi_chain;
 typedef struct {
     uint32_t arith;          /* DSPI_ARITH_F32_FUSED or DSPI_ARITH_F32_STRICT                       */

@@ -85,3 +85,36 @@ def test_bad_arguments_are_rejected(lib):
     assert lib.dspi_eq_create(C.byref(h), C.byref(desc)) == -22
     assert lib.dspi_eq_create(None, None) == -22
     assert b"" != lib.dspi_last_error()
+
+
+def test_chain_parameter_functions_match_the_reference(lib, oracle, refs):
+    """crossfeed / leveller / loudness / volume parameter functions, bit-exact vs the strict reference build"""
+    import ctypes as C
+    from tests.util import field_bits
+    for fs in (44100.0, 48000.0, 96000.0):
+        for preset in range(4):
+            for itd in (0, 1):
+                mine = api.crossfeed_coefficients(fs, True, itd, preset, 1234.0, 7.0)
+                st = np.zeros(1, L.XFEED_F32)
+                refs["f32s"].lib.ref_xfeed_coeffs(st.ctypes.data, 1, itd, preset, 1234.0, 7.0, fs)
+                assert np.array_equal(field_bits(np.array([mine])), field_bits(st))
+        assert not np.any(field_bits(np.array([api.crossfeed_coefficients(fs, enabled=False)])))
+        for speed in (0, 1, 2, 9):
+            mine = api.leveller_coefficients(fs, 70.0, speed, 40.0, -120.0)
+            want = np.zeros(1, L.LEV_COEFFS)
+            refs["f32s"].lib.ref_lev_coeffs(want.ctypes.data, 70.0, speed, 40.0, -120.0, fs)
+            assert np.array_equal(field_bits(np.array([mine])), field_bits(want))
+        for ref_spl, inten in ((83.0, 100.0), (60.0, 35.0), (130.0, 200.0)):
+            want = np.zeros((L.LOUD_STEPS, 2), L.LOUD_F32)
+            refs["f32s"].lib.ref_loud_table(want.ctypes.data, ref_spl, inten, fs)
+            assert np.array_equal(field_bits(api.loudness_table(fs, ref_spl, inten)), field_bits(want))
+    # KATs the reference states: 4.5 dB feed -> G = 0.373 (crossfeed.c:65); 0 dB host volume -> int16 -32768
+    g = api.crossfeed_coefficients(48000.0, preset=0)
+    assert abs(float(g["lp_a0"]) / (1.0 - float(g["lp_b1"])) - 0.373) < 1e-3
+    assert api.host_volume(0) == (-32768, 60) and api.host_volume(-20 * 256) == (0x0CCD, 40) and api.host_volume(-32768)[0] == 0
+    for v in range(-70 * 256, 1 * 256, 97):
+        assert api.host_volume(v)[0] == oracle.lib.orc_host_vol_mul(v, None)
+    for ms in (0.0, 3.3, 42.0, 85.4, 500.0, -1.0):
+        for fs in (48000.0, 96000.0):
+            for last in (0, 1):
+                assert api.delay_samples(ms, fs, last) == refs["f32s"].lib.ref_delay_samples(ms, fs, last)
