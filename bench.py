@@ -347,7 +347,7 @@ def main():
             dt = float(t.item())
         e2e = {"value": float(Cn) * T * n_e2e * world / dt, "unit": "samples/s", "h2d_bytes_per_step": Cn * T * 4,
                "d2h_bytes_per_step": Cn * T * 4, "steps": n_e2e,
-               "path": "dspi_eq_process_host: pinned host [C][T] -> chunked cudaMemcpy2DAsync H2D / kernel / D2H on 3 streams"}
+               "path": "dspi_eq_process_host: pinned host [C][T] -> channel-chunked cudaMemcpyAsync H2D / kernel / D2H on 3 streams"}
         pin.free()
 
     cpu = None

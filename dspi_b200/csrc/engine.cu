@@ -256,32 +256,35 @@ static int make_tmap(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint3
     return DSPI_OK;
 }
 
-// launch over all channels of the engine on `stream`
-static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStream_t stream)
+// launch over groups [g0, g0 + ng) of the engine on `stream`; d_samples points at the first row of
+// group g0 and holds `n_rows` valid rows
+static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint32_t g0, uint32_t ng, uint32_t n_rows, cudaStream_t stream)
 {
     dspi::EqLaunch a;
     memset(&a, 0, sizeof(a));
     const bool tma_ok = (ld % 4 == 0) && (((uintptr_t)d_samples & 15) == 0);
     if (tma_ok) {
-        if (e->tm_ptr != d_samples || e->tm_T != T || e->tm_ld != ld || e->tm_rows != e->desc.n_channels) {
-            int rc = make_tmap(e, d_samples, T, ld, e->desc.n_channels, &e->tmap);
+        if (e->tm_ptr != d_samples || e->tm_T != T || e->tm_ld != ld || e->tm_rows != n_rows) {
+            int rc = make_tmap(e, d_samples, T, ld, n_rows, &e->tmap);
             if (rc) return rc;
-            e->tm_ptr = d_samples; e->tm_T = T; e->tm_ld = ld; e->tm_rows = e->desc.n_channels;
+            e->tm_ptr = d_samples; e->tm_T = T; e->tm_ld = ld; e->tm_rows = n_rows;
         }
         a.tmap = e->tmap;
     }
+    const bool q28 = e->desc.arith == DSPI_ARITH_Q28;
     a.samples = d_samples;
     a.ld = ld;
-    a.coef = e->d_coef;
-    a.modes = e->d_modes;
-    a.n_groups = e->n_groups;
-    a.n_rows = e->desc.n_channels;
+    a.coef = q28 ? (void *)((int32_t *)e->d_coef + (size_t)g0 * DSPI_MAX_BANDS * 20 * 32)
+                 : (void *)((float *)e->d_coef + (size_t)g0 * DSPI_MAX_BANDS * 8 * 32 * e->cpl);
+    a.modes = e->d_modes ? e->d_modes + (size_t)g0 * e->rows : nullptr;
+    a.n_groups = ng;
+    a.n_rows = n_rows;
     a.T = T;
     a.n_bands = e->desc.n_bands;
     a.use_tma = tma_ok ? 1u : 0u;
     if (const char *v = getenv("DSPI_DBG")) a.dbg = (uint32_t)atoi(v);
     cudaError_t err;
-    if (e->desc.arith == DSPI_ARITH_Q28) err = dspi::launch_eq_q28(a, stream);
+    if (q28) err = dspi::launch_eq_q28(a, stream);
     else err = dspi::launch_eq_f32(a, e->desc.arith == DSPI_ARITH_F32_FUSED, e->cpl, stream);
     if (err != cudaSuccess) return fail(DSPI_ECUDA, "EQ kernel launch: %s", cudaGetErrorString(err));
     e->launches++;
@@ -294,7 +297,7 @@ int dspi_eq_process_device(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld)
     if (T == 0) return DSPI_OK;
     if (ld < T) return fail(DSPI_EINVAL, "row stride %u < T %u", ld, T);
     CU_OK(cudaSetDevice(e->desc.device));
-    return launch_eq(e, d_samples, T, ld, e->stream);
+    return launch_eq(e, d_samples, T, ld, 0, e->n_groups, e->desc.n_channels, e->stream);
 }
 
 int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T)
@@ -303,13 +306,15 @@ int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T)
     if (T == 0) return DSPI_OK;
     CU_OK(cudaSetDevice(e->desc.device));
     const uint32_t C = e->desc.n_channels;
-    // time-chunked pipeline: all channels x Tc samples per step, so every launch fills the GPU and the
-    // filter state is carried from chunk to chunk exactly as from packet to packet in the firmware.
-    uint32_t Tc = (uint32_t)(((size_t)96 << 20) / ((size_t)C * 4));
-    Tc = (Tc / 32) * 32;
-    if (Tc < 32) Tc = 32;
-    if (Tc >= T) Tc = (T + 3) & ~3u;
-    const size_t need = (size_t)C * Tc * 4;
+    // channel-chunked pipeline: rows [c0, c1) x T are contiguous in the caller's [C][T] array, so every
+    // copy is one large 1-D transfer at full PCIe rate; H2D, kernel and D2H of consecutive chunks
+    // overlap on three streams.  Channels are independent, so chunk order and size change no bit.
+    const uint32_t ld = (T + 3) & ~3u;                                      // device rows padded for TMA
+    uint32_t cc = (uint32_t)(((size_t)96 << 20) / ((size_t)ld * 4));
+    cc = cc / e->rows * e->rows;
+    if (cc < e->rows) cc = e->rows;
+    if (cc > e->c_pad) cc = e->c_pad;
+    const size_t need = (size_t)cc * ld * 4;
     if (need > e->stage_bytes) {
         for (int i = 0; i < kHostBufs; i++) {
             if (e->d_stage[i]) { cudaFree(e->d_stage[i]); e->d_stage[i] = nullptr; }
@@ -320,23 +325,23 @@ int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T)
         }
         e->stage_bytes = need;
     }
-    const uint32_t nchunks = (T + Tc - 1) / Tc;
+    const uint32_t nchunks = (C + cc - 1) / cc;
     char *host = (char *)h_samples;
     for (uint32_t k = 0; k < nchunks; k++) {
         const int b = k % kHostBufs;
-        const uint32_t t0 = k * Tc, n = (T - t0 < Tc) ? (T - t0) : Tc;
+        const uint32_t c0 = k * cc, n = (C - c0 < cc) ? (C - c0) : cc;
+        char *hp = host + (size_t)c0 * T * 4;
         if (k >= (uint32_t)kHostBufs) CU_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_out[b], 0));       // buffer drained
-        CU_OK(cudaMemcpy2DAsync(e->d_stage[b], (size_t)Tc * 4, host + (size_t)t0 * 4, (size_t)T * 4, (size_t)n * 4, C,
-                                cudaMemcpyHostToDevice, e->s_h2d));
+        if (ld == T) CU_OK(cudaMemcpyAsync(e->d_stage[b], hp, (size_t)n * T * 4, cudaMemcpyHostToDevice, e->s_h2d));
+        else CU_OK(cudaMemcpy2DAsync(e->d_stage[b], (size_t)ld * 4, hp, (size_t)T * 4, (size_t)T * 4, n, cudaMemcpyHostToDevice, e->s_h2d));
         CU_OK(cudaEventRecord(e->ev_in[b], e->s_h2d));
         CU_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
-        e->tm_ptr = nullptr;                                                                      // chunk geometry changes at the tail
-        int rc = launch_eq(e, e->d_stage[b], n, Tc, e->stream);
+        int rc = launch_eq(e, e->d_stage[b], T, ld, c0 / e->rows, (n + e->rows - 1) / e->rows, n, e->stream);
         if (rc) return rc;
         CU_OK(cudaEventRecord(e->ev_done[b], e->stream));
         CU_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[b], 0));
-        CU_OK(cudaMemcpy2DAsync(host + (size_t)t0 * 4, (size_t)T * 4, e->d_stage[b], (size_t)Tc * 4, (size_t)n * 4, C,
-                                cudaMemcpyDeviceToHost, e->s_d2h));
+        if (ld == T) CU_OK(cudaMemcpyAsync(hp, e->d_stage[b], (size_t)n * T * 4, cudaMemcpyDeviceToHost, e->s_d2h));
+        else CU_OK(cudaMemcpy2DAsync(hp, (size_t)T * 4, e->d_stage[b], (size_t)ld * 4, (size_t)T * 4, n, cudaMemcpyDeviceToHost, e->s_d2h));
         CU_OK(cudaEventRecord(e->ev_out[b], e->s_d2h));
     }
     CU_OK(cudaStreamSynchronize(e->s_d2h));
