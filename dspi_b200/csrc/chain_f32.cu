@@ -456,15 +456,20 @@ chain_pdm_kernel(ChainDev d, uint32_t F, uint32_t *__restrict__ pdm_out)
             const int32_t in = raw - err_acc;
             const int32_t dither = (15778 * in - 31556 * x1 + 15778 * x2 + 31531 * y1 - 15580 * y2) >> 14;   // :98-99
             x2 = x1; x1 = in; y2 = y1; y1 = dither;
+            // :372-378, re-associated so that only three dependent integer ops separate two decisions:
+            //   s = err2 + dither (the comparator input), m = s >> 31 (all ones when the bit is 0),
+            //   -fb = ~m & -65535;  err1 += target - fb;  s += err1 - fb   (== err2' + dither)
             uint32_t word = 0;
+            int32_t s = err2 + dither;
 #pragma unroll
-            for (int k = 0; k < 32; k++) {                                   // :372-378
-                const bool bit = (err2 + dither) >= 0;
-                const int32_t fb = bit ? 65535 : 0;
-                word = (word << 1) | (bit ? 1u : 0u);
-                err1 += target - fb;
-                err2 += err1 - fb;
+            for (int k = 0; k < 32; k++) {
+                const int32_t m = s >> 31;
+                const int32_t nfb = ~m & -65535;
+                word = __funnelshift_l((uint32_t)~m, word, 1);               // (word << 1) | bit, MSB first
+                err1 += target + nfb;
+                s += err1 + nfb;
             }
+            err2 = s - dither;
             words[chunk] = word;
         }
         err1 -= err1 >> 16;                                                  // :396-397

@@ -185,21 +185,21 @@ __device__ __forceinline__ void svf_tile(const V (&x)[N], V (&y)[N], const V (&c
 // Same operation sequences as above in their natural (reference) form.
 template <bool FUSED>
 __device__ __noinline__ float2 slow_band(float *xs, int n, uint32_t mode, float c0, float c1, float c2, float c3, float c4, float c5,
-                                         float st0, float st1)
+                                         float st0, float st1, int stride = 1)
 {
     if (mode == kModeTdf2) {
         for (int i = 0; i < n; i++) {
-            const float in = xs[i];
+            const float in = xs[i * stride];
             const float out = madd<FUSED>(c0, in, st0);
             const float m = __fmul_rn(c3, out);
             st0 = __fadd_rn(madd<FUSED>(c1, in, m), st1);
             const float nn = __fmul_rn(c4, out);
             st1 = madd<FUSED>(c2, in, nn);
-            xs[i] = out;
+            xs[i * stride] = out;
         }
     } else if (mode >= kModeSvfLP) {
         for (int i = 0; i < n; i++) {
-            const float in = xs[i];
+            const float in = xs[i * stride];
             const float v3 = __fadd_rn(in, -st1);
             const float p = __fmul_rn(c1, v3);
             float t, v1, v2;
@@ -219,7 +219,7 @@ __device__ __noinline__ float2 slow_band(float *xs, int n, uint32_t mode, float 
             else if (mode == kModeSvfPK) y = madd<FUSED>(c4, v1, in);
             else if (mode == kModeSvfHP) y = __fadd_rn(madd<FUSED>(c4, v1, in), -v2);
             else y = madd<FUSED>(c5, v2, madd<FUSED>(c3, in, __fmul_rn(c4, v1)));
-            xs[i] = y;
+            xs[i * stride] = y;
         }
     }
     return make_float2(st0, st1);
@@ -356,6 +356,55 @@ struct EqBank {
             }
         }
         static_assert(NB % 2 == 0, "results must land back in x");
+    }
+
+    // one band over n samples (n % 4 == 0) stored as a lane-private column: sample i at col[i * 32]
+    template <int MODE>
+    __device__ __forceinline__ void band_loop(V *col, int n, const V (&cc)[6], V &s0, V &s1, const V nz)
+    {
+#pragma unroll 2
+        for (int i = 0; i < n; i += 4) {
+            V x[4], y[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) x[j] = col[(i + j) * 32];
+            if constexpr (MODE == (int)kModeTdf2) tdf2_tile<FUSED>(x, y, cc, s0, s1, nz);
+            else svf_tile<FUSED, MODE>(x, y, cc, s0, s1, nz);
+#pragma unroll
+            for (int j = 0; j < 4; j++) col[(i + j) * 32] = y[j];
+        }
+    }
+
+    // Band-outer pass over a shared-memory tile in column layout (the reference's own loop order,
+    // dsp_pipeline.c:286-364): topology dispatch happens once per band per tile, each band is a
+    // small rolled loop (stays in the instruction cache), samples travel LDS.64 -> registers ->
+    // STS.64 between bands.  `col` already includes this lane's offset.
+    __device__ __forceinline__ void run_columns(V *col, int n, const V nz)
+    {
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            if (b >= (int)nb_active) break;
+            const uint32_t m = (uint32_t)(mode_w >> (4 * b)) & 15u;
+            if (((uni >> b) & 1u) && (n & 3) == 0) {
+                if (m == kModeTdf2) band_loop<(int)kModeTdf2>(col, n, c[b], st[b][0], st[b][1], nz);
+                else if (m == kModeSvfPK) band_loop<kMixPK>(col, n, c[b], st[b][0], st[b][1], nz);
+                else if (m == kModeSvfSH) band_loop<kMixSH>(col, n, c[b], st[b][0], st[b][1], nz);
+                else if (m == kModeSvfLP) band_loop<kMixLP>(col, n, c[b], st[b][0], st[b][1], nz);
+                else if (m == kModeSvfHP) band_loop<kMixHP>(col, n, c[b], st[b][0], st[b][1], nz);
+            } else {
+                float ns0[CPL], ns1[CPL];
+#pragma unroll
+                for (int h = 0; h < CPL; h++) {
+                    const uint32_t mh = (uint32_t)(mode_h[h] >> (4 * b)) & 15u;
+                    const float2 ns = slow_band<FUSED>(reinterpret_cast<float *>(col) + h, n, mh, Lanes<V>::get(c[b][0], h), Lanes<V>::get(c[b][1], h),
+                                                       Lanes<V>::get(c[b][2], h), Lanes<V>::get(c[b][3], h), Lanes<V>::get(c[b][4], h),
+                                                       Lanes<V>::get(c[b][5], h), Lanes<V>::get(st[b][0], h), Lanes<V>::get(st[b][1], h), 32 * CPL);
+                    ns0[h] = ns.x;
+                    ns1[h] = ns.y;
+                }
+                v_make(st[b][0], ns0);
+                v_make(st[b][1], ns1);
+            }
+        }
     }
 };
 

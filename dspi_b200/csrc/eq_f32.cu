@@ -100,39 +100,78 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
         }
 
         const int tile_valid = min((int)kTileT, (int)(T - tile * kTileT));
+        if (bank.all_tdf2 && tile_valid == kTileT && !(dbg & 4u)) {
+            // ---- all-biquad warps: register tiles of kSub samples, straight-line over the 10 bands ----
 #pragma unroll 1
-        for (int sub = 0; sub < kTileT / kSub; sub++) {
-            const int nvalid = min(kSub, tile_valid - sub * kSub);
-            if (nvalid <= 0) break;
-            // two 16-byte chunks per row per sub-tile; chunk index XOR (row & 7)
-            V x[kSub];
-            float4 q[CPL][2];
+            for (int sub = 0; sub < kTileT / kSub; sub++) {
+                // two 16-byte chunks per row per sub-tile; chunk index XOR (row & 7)
+                V x[kSub];
+                float4 q[CPL][2];
+#pragma unroll
+                for (int h = 0; h < CPL; h++) {
+                    const uint8_t *row = buf + (lane + 32 * h) * 128;
+                    q[h][0] = *reinterpret_cast<const float4 *>(row + (((2 * sub) << 4) ^ sw));
+                    q[h][1] = *reinterpret_cast<const float4 *>(row + (((2 * sub + 1) << 4) ^ sw));
+                }
+#pragma unroll
+                for (int i = 0; i < kSub; i++) {
+                    float part[CPL];
+#pragma unroll
+                    for (int h = 0; h < CPL; h++) {
+                        const float4 &qq = q[h][i >> 2];
+                        part[h] = (i & 3) == 0 ? qq.x : (i & 3) == 1 ? qq.y : (i & 3) == 2 ? qq.z : qq.w;
+                    }
+                    v_make(x[i], part);
+                }
+                if (!(dbg & 1u)) bank.run(x, kSub, nz);            // DSPI_DBG=1: data path only
+#pragma unroll
+                for (int h = 0; h < CPL; h++) {
+                    uint8_t *row = buf + (lane + 32 * h) * 128;
+                    *reinterpret_cast<float4 *>(row + (((2 * sub) << 4) ^ sw)) =
+                        make_float4(Lanes<V>::get(x[0], h), Lanes<V>::get(x[1], h), Lanes<V>::get(x[2], h), Lanes<V>::get(x[3], h));
+                    *reinterpret_cast<float4 *>(row + (((2 * sub + 1) << 4) ^ sw)) =
+                        make_float4(Lanes<V>::get(x[4], h), Lanes<V>::get(x[5], h), Lanes<V>::get(x[6], h), Lanes<V>::get(x[7], h));
+                }
+            }
+        } else {
+            // ---- any other topology: band-outer over the tile, re-laid out in place as lane-private
+            //      columns of CPL-vectors (sample n of this lane at col[n * 32]) ----
+            float4 q[CPL][8];
 #pragma unroll
             for (int h = 0; h < CPL; h++) {
                 const uint8_t *row = buf + (lane + 32 * h) * 128;
-                q[h][0] = *reinterpret_cast<const float4 *>(row + (((2 * sub) << 4) ^ sw));
-                q[h][1] = *reinterpret_cast<const float4 *>(row + (((2 * sub + 1) << 4) ^ sw));
-            }
 #pragma unroll
-            for (int i = 0; i < kSub; i++) {
+                for (int k = 0; k < 8; k++) q[h][k] = *reinterpret_cast<const float4 *>(row + ((k << 4) ^ sw));
+            }
+            __syncwarp();                                       // every row is in registers before columns overwrite them
+            V *col = reinterpret_cast<V *>(buf) + lane;
+#pragma unroll
+            for (int n = 0; n < kTileT; n++) {
                 float part[CPL];
 #pragma unroll
                 for (int h = 0; h < CPL; h++) {
-                    const float4 &qq = q[h][i >> 2];
-                    part[h] = (i & 3) == 0 ? qq.x : (i & 3) == 1 ? qq.y : (i & 3) == 2 ? qq.z : qq.w;
+                    const float4 &qq = q[h][n >> 2];
+                    part[h] = (n & 3) == 0 ? qq.x : (n & 3) == 1 ? qq.y : (n & 3) == 2 ? qq.z : qq.w;
                 }
-                v_make(x[i], part);
+                V v;
+                v_make(v, part);
+                col[n * 32] = v;
             }
-
-            if (!(dbg & 1u)) bank.run(x, nvalid, nz);           // DSPI_DBG=1: data path only
-
+            if (!(dbg & 1u)) bank.run_columns(col, tile_valid, nz);
+            float back[CPL][kTileT];
+#pragma unroll
+            for (int n = 0; n < kTileT; n++) {
+                const V v = col[n * 32];
+#pragma unroll
+                for (int h = 0; h < CPL; h++) back[h][n] = Lanes<V>::get(v, h);
+            }
+            __syncwarp();
 #pragma unroll
             for (int h = 0; h < CPL; h++) {
                 uint8_t *row = buf + (lane + 32 * h) * 128;
-                *reinterpret_cast<float4 *>(row + (((2 * sub) << 4) ^ sw)) =
-                    make_float4(Lanes<V>::get(x[0], h), Lanes<V>::get(x[1], h), Lanes<V>::get(x[2], h), Lanes<V>::get(x[3], h));
-                *reinterpret_cast<float4 *>(row + (((2 * sub + 1) << 4) ^ sw)) =
-                    make_float4(Lanes<V>::get(x[4], h), Lanes<V>::get(x[5], h), Lanes<V>::get(x[6], h), Lanes<V>::get(x[7], h));
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    *reinterpret_cast<float4 *>(row + ((k << 4) ^ sw)) = make_float4(back[h][4 * k], back[h][4 * k + 1], back[h][4 * k + 2], back[h][4 * k + 3]);
             }
         }
 
