@@ -117,7 +117,7 @@ __device__ __forceinline__ float gain_computer(float x_db, float threshold, floa
 // ---------------------------------------------------------------------------------------------
 template <bool FUSED, int NB>
 __global__ void __launch_bounds__(128, 1)
-chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t fpp)
+chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F)
 {
     extern __shared__ float smem[];                       // [warps][kPkt][32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,7 +127,6 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
     const bool live = inst < d.N;
     float *xs = smem + (size_t)warp * kPkt * 32 + lane;   // xs[t * 32]
     const uint32_t Np = d.N_pad;
-    const uint32_t F = n_packets * fpp;
 
     const uint8_t flags = d.flags[inst];
     const bool loud_on = flags & F_LOUD, lev_on = flags & F_LEV, xf_on = flags & F_XFEED;
@@ -171,7 +170,7 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
 
     float peak_in = 0.0f;
     uint16_t clip = 0;
-    for (uint32_t p = 0; p < n_packets; p++) {
+    for (uint32_t p = p0; p < p0 + n_packets; p++) {
         const uint32_t f0 = p * fpp;
         // ---- PASS 1 + loudness + PASS 2 (master EQ), register tiles of 8 ----
         for (uint32_t t0 = 0; t0 < fpp; t0 += kSub) {
@@ -330,8 +329,8 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
 // outputs: matrix, per-output EQ, gain, delay, peaks, 24-bit conversion / Q28 for the modulator
 // ---------------------------------------------------------------------------------------------
 template <bool FUSED, int NB>
-__global__ void __launch_bounds__(128, 1)
-chain_out_kernel(ChainDev d, uint32_t n_packets, uint32_t fpp, int32_t *__restrict__ spdif_out)
+__global__ void __launch_bounds__(128, 3)
+chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F, int32_t *__restrict__ spdif_out)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -341,7 +340,6 @@ chain_out_kernel(ChainDev d, uint32_t n_packets, uint32_t fpp, int32_t *__restri
     const uint32_t inst = (wid % groups) * 32 + lane;
     const bool live = inst < d.N;
     const uint32_t Np = d.N_pad;
-    const uint32_t F = n_packets * fpp;
 
     const uint8_t of = d.o_flags[o * Np + inst];
     const bool enabled = of & O_ENABLED, mute = of & O_MUTE, pair_off = of & O_PAIR_OFF;
@@ -367,7 +365,7 @@ chain_out_kernel(ChainDev d, uint32_t n_packets, uint32_t fpp, int32_t *__restri
     int32_t *my_spdif = nullptr;
     if (!is_sub && spdif_out && live) my_spdif = spdif_out + (((size_t)inst * 4 + (o >> 1)) * F) * 2 + (o & 1);
 
-    for (uint32_t p = 0; p < n_packets; p++) {
+    for (uint32_t p = p0; p < p0 + n_packets; p++) {
         const uint32_t f0 = p * fpp;
         float pk = 0.0f;
         uint32_t w = widx;
@@ -391,17 +389,34 @@ chain_out_kernel(ChainDev d, uint32_t n_packets, uint32_t fpp, int32_t *__restri
             bank_run_masked<FUSED, NB>(bank, x, nvalid, skip_eq);
 #pragma unroll
             for (int i = 0; i < kSub; i++) {
-                if (i >= nvalid) break;
-                float v = x[i];
                 if (enabled) {                                               // :885-894
-                    if (gain == 0.0f) v = 0.0f;
-                    else if (gain != 1.0f) v = __fmul_rn(v, gain);
+                    if (gain == 0.0f) x[i] = 0.0f;
+                    else if (gain != 1.0f) x[i] = __fmul_rn(x[i], gain);
                 }
-                if (delay_on) {                                              // :902-909 write, then read
-                    ring[(size_t)w * Np] = v;
-                    v = ring[(size_t)((w - (uint32_t)dly) & (kMaxDelay - 1)) * Np];
+            }
+            if (delay_on) {                                                  // :902-909: write, then read, per sample
+                if (dly <= kMaxDelay - kSub) {
+                    // all writes of the tile first, then all (independent) reads: one exposed memory
+                    // latency per tile instead of one per sample.  Safe because a read can only land on a
+                    // slot written LATER in the same tile when dly > MAX_DELAY - kSub.
+#pragma unroll
+                    for (int i = 0; i < kSub; i++)
+                        if (i < nvalid) ring[(size_t)((w + i) & (kMaxDelay - 1)) * Np] = x[i];
+#pragma unroll
+                    for (int i = 0; i < kSub; i++)
+                        if (i < nvalid) x[i] = ring[(size_t)((w + i - (uint32_t)dly) & (kMaxDelay - 1)) * Np];
+                } else {
+                    for (int i = 0; i < nvalid; i++) {
+                        ring[(size_t)((w + i) & (kMaxDelay - 1)) * Np] = x[i];
+                        x[i] = ring[(size_t)((w + i - (uint32_t)dly) & (kMaxDelay - 1)) * Np];
+                    }
                 }
-                w = (w + 1) & (kMaxDelay - 1);
+            }
+            w = (w + nvalid) & (kMaxDelay - 1);
+#pragma unroll
+            for (int i = 0; i < kSub; i++) {
+                if (i >= nvalid) break;
+                const float v = x[i];
                 const float a = fabsf(v);
                 if (a > pk) pk = a;
                 if (is_sub) {
@@ -432,7 +447,7 @@ chain_out_kernel(ChainDev d, uint32_t n_packets, uint32_t fpp, int32_t *__restri
 // delta-sigma PDM, pdm_generator.c:351-397 (steady state) + :62-108
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-chain_pdm_kernel(ChainDev d, uint32_t F, uint32_t *__restrict__ pdm_out)
+chain_pdm_kernel(ChainDev d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
     const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= d.N) return;
@@ -442,7 +457,7 @@ chain_pdm_kernel(ChainDev d, uint32_t F, uint32_t *__restrict__ pdm_out)
     int32_t x1 = d.pdm[2 * Np + inst], x2 = d.pdm[3 * Np + inst], y1 = d.pdm[4 * Np + inst], y2 = d.pdm[5 * Np + inst];
     int32_t err_acc = d.pdm[6 * Np + inst];
     uint32_t rng = (uint32_t)d.pdm[7 * Np + inst], fade = (uint32_t)d.pdm[8 * Np + inst];
-    for (uint32_t f = 0; f < F; f++) {
+    for (uint32_t f = f_begin; f < f_end; f++) {
         int32_t pcm = d.subq[(size_t)f * Np + inst] >> 14;                   // :352
         pcm = max(-29500, min(29500, pcm));                                  // :353-354
         if (fade < 1024u) { pcm = (pcm * (int32_t)fade) >> 10; fade++; }     // :357-360
@@ -566,7 +581,8 @@ using dspi::fail;
 struct dspi_chain {
     dspi_chain_desc desc;
     ChainDev d;
-    cudaStream_t stream;
+    cudaStream_t stream, s_pdm;
+    cudaEvent_t ev_slice[4], ev_pdm;
     dspi_biquad_f32 *d_aos;          // [N_pad][11][12] instance-major mirror of filters[][]
     std::vector<void *> allocs;
     uint64_t launches;
@@ -616,31 +632,38 @@ template <bool FUSED>
 int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t fpp, int32_t *d_spdif, uint32_t *d_pdm,
                  dspi_status *d_status)
 {
-    const ChainDev &d = c->d;
     const uint32_t F = n_packets * fpp;
-    {
-        auto kern = dspi::chain_front_kernel<FUSED, 10>;
-        const size_t smem = (size_t)4 * dspi::kPkt * 32 * 4;
-        static bool configured = false;
-        if (!configured) { CU_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
-        const uint32_t warps = d.N_pad / 16;
-        kern<<<(warps + 3) / 4, 128, smem, c->stream>>>(d, (const uint8_t *)d_pcm, bit_depth, n_packets, fpp);
+    auto front = dspi::chain_front_kernel<FUSED, 10>;
+    const size_t smem = (size_t)4 * dspi::kPkt * 32 * 4;
+    static bool configured = false;
+    if (!configured) { CU_OK(cudaFuncSetAttribute(front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    // The modulator is one serial chain per instance (256 decisions per frame) and fills only a fraction
+    // of the machine, so the call is cut into packet slices: the PDM kernel of slice k runs on a second
+    // stream while front + outputs of slice k+1 run on the engine stream.  All state lives in HBM
+    // between slices, so the slicing changes no bit.
+    const uint32_t n_slices = n_packets < 4 ? n_packets : 4;
+    for (uint32_t sl = 0; sl < n_slices; sl++) {
+        const uint32_t p0 = (uint32_t)((uint64_t)n_packets * sl / n_slices), p1 = (uint32_t)((uint64_t)n_packets * (sl + 1) / n_slices);
+        const ChainDev d = c->d;
+        const uint32_t fwarps = d.N_pad / 16, owarps = d.N_pad / 32 * dspi::kOuts;
+        front<<<(fwarps + 3) / 4, 128, smem, c->stream>>>(d, (const uint8_t *)d_pcm, bit_depth, p0, p1 - p0, fpp, F);
         CU_OK(cudaGetLastError());
-    }
-    {
-        const uint32_t warps = d.N_pad / 32 * dspi::kOuts;
-        dspi::chain_out_kernel<FUSED, 10><<<(warps + 3) / 4, 128, 0, c->stream>>>(d, n_packets, fpp, d_spdif);
+        dspi::chain_out_kernel<FUSED, 10><<<(owarps + 3) / 4, 128, 0, c->stream>>>(d, p0, p1 - p0, fpp, F, d_spdif);
         CU_OK(cudaGetLastError());
+        std::swap(c->d.widx_in, c->d.widx_out);
+        CU_OK(cudaEventRecord(c->ev_slice[sl], c->stream));
+        CU_OK(cudaStreamWaitEvent(c->s_pdm, c->ev_slice[sl], 0));
+        dspi::chain_pdm_kernel<<<(d.N + 127) / 128, 128, 0, c->s_pdm>>>(d, p0 * fpp, p1 * fpp, F, d_pdm);
+        CU_OK(cudaGetLastError());
+        c->launches += 3;
     }
-    dspi::chain_pdm_kernel<<<(d.N + 127) / 128, 128, 0, c->stream>>>(d, F, d_pdm);
-    CU_OK(cudaGetLastError());
-    c->launches += 3;
+    CU_OK(cudaEventRecord(c->ev_pdm, c->s_pdm));
+    CU_OK(cudaStreamWaitEvent(c->stream, c->ev_pdm, 0));         // later work on the engine stream sees the PDM words
     if (d_status) {
-        dspi::chain_status_kernel<<<(d.N + 127) / 128, 128, 0, c->stream>>>(d, d_status);
+        dspi::chain_status_kernel<<<(c->d.N + 127) / 128, 128, 0, c->stream>>>(c->d, d_status);
         CU_OK(cudaGetLastError());
         c->launches++;
     }
-    std::swap(c->d.widx_in, c->d.widx_out);
     return DSPI_OK;
 }
 
@@ -663,6 +686,9 @@ int dspi_chain_destroy(dspi_chain *c)
     if (!c) return DSPI_OK;
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->s_pdm) { cudaStreamSynchronize(c->s_pdm); cudaStreamDestroy(c->s_pdm); }
+    for (int i = 0; i < 4; i++) if (c->ev_slice[i]) cudaEventDestroy(c->ev_slice[i]);
+    if (c->ev_pdm) cudaEventDestroy(c->ev_pdm);
     for (void *p : c->allocs) cudaFree(p);
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_spdif) cudaFree(c->d_spdif);
@@ -689,6 +715,11 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     CU_OK(cudaSetDevice(desc->device));
     dspi_chain *c = new (std::nothrow) dspi_chain();
     if (!c) return fail(DSPI_ENOMEM, "host allocation failed");
+    c->stream = c->s_pdm = nullptr;
+    c->ev_pdm = nullptr;
+    for (int i = 0; i < 4; i++) c->ev_slice[i] = nullptr;
+    c->d_aos = nullptr; c->launches = 0; c->d_pcm = nullptr; c->pcm_bytes = 0; c->d_spdif = nullptr; c->spdif_bytes = 0;
+    c->d_pdmout = nullptr; c->pdmout_bytes = 0; c->d_status = nullptr;
     c->desc = *desc;
     ChainDev &d = c->d;
     memset(&d, 0, sizeof(d));
@@ -698,6 +729,9 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     d.max_frames = desc->max_frames;
     const size_t Np = d.N_pad;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_pdm, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev_slice[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pdm, cudaEventDisableTiming);
 #define TRY(x) if (e == cudaSuccess) e = (x)
     TRY(dev_alloc(c, &c->d_aos, Np * dspi::kRoles * DSPI_MAX_BANDS));
     TRY(dev_alloc(c, &d.coef, Np * dspi::kRoles * DSPI_MAX_BANDS * 8));
