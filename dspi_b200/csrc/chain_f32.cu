@@ -52,7 +52,7 @@ struct ChainDev {
     float *xf;                                    // [7][N_pad] lp_a0 lp_b1 lp_L lp_R ap_a ap_L ap_R
     float *lev_c; float *lev_s; uint32_t *lev_idx; float *lev_la;   // [9][N_pad], [5][N_pad], [N_pad], [2][480][N_pad]
     float *o_gl, *o_gr, *o_gain; uint8_t *o_flags; int32_t *o_dly;  // [9][N_pad]
-    float *dline; uint32_t *widx_in, *widx_out;   // [9][4096][N_pad], [N_pad]
+    float *dline; uint32_t *widx_in, *widx_out;   // [9][N_pad][4096], [N_pad]
     int32_t *pdm;                                 // [9][N_pad] err1 err2 x1 x2 y1 y2 err_acc rng fade_in_pos
     uint16_t *peaks; uint16_t *clip;              // [11][N_pad], [N_pad]
     float *master; int32_t *subq;                 // [2][max_frames][N_pad], [max_frames][N_pad]
@@ -348,7 +348,7 @@ chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint
     const bool delay_on = (d.flags[inst] & F_ANY_DELAY) && dly > 0;          // usb_audio.c:898-901
     const bool any_delay = d.flags[inst] & F_ANY_DELAY;
     uint32_t widx = d.widx_in[inst];
-    float *ring = d.dline + (size_t)o * kMaxDelay * Np + inst;
+    float *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;     // one contiguous ring per (output, instance)
 
     EqBank<float, FUSED, NB> bank;
     float *my_coef = const_cast<float *>(eq_base(d, 2 + o, inst));
@@ -401,14 +401,14 @@ chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint
                     // slot written LATER in the same tile when dly > MAX_DELAY - kSub.
 #pragma unroll
                     for (int i = 0; i < kSub; i++)
-                        if (i < nvalid) ring[(size_t)((w + i) & (kMaxDelay - 1)) * Np] = x[i];
+                        if (i < nvalid) ring[(w + i) & (kMaxDelay - 1)] = x[i];
 #pragma unroll
                     for (int i = 0; i < kSub; i++)
-                        if (i < nvalid) x[i] = ring[(size_t)((w + i - (uint32_t)dly) & (kMaxDelay - 1)) * Np];
+                        if (i < nvalid) x[i] = ring[(w + i - (uint32_t)dly) & (kMaxDelay - 1)];
                 } else {
                     for (int i = 0; i < nvalid; i++) {
-                        ring[(size_t)((w + i) & (kMaxDelay - 1)) * Np] = x[i];
-                        x[i] = ring[(size_t)((w + i - (uint32_t)dly) & (kMaxDelay - 1)) * Np];
+                        ring[(w + i) & (kMaxDelay - 1)] = x[i];
+                        x[i] = ring[(w + i - (uint32_t)dly) & (kMaxDelay - 1)];
                     }
                 }
             }
@@ -729,7 +729,11 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     d.max_frames = desc->max_frames;
     const size_t Np = d.N_pad;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->s_pdm, cudaStreamNonBlocking);
+    {
+        int lo = 0, hi = 0;                                  // the modulator stream gets the highest priority: its few CTAs
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);          // are placed first whenever an SM frees a slot
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->s_pdm, cudaStreamNonBlocking, hi);
+    }
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev_slice[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pdm, cudaEventDisableTiming);
 #define TRY(x) if (e == cudaSuccess) e = (x)
