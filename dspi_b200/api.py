@@ -26,6 +26,9 @@ SYMBOLS = [
     "dspi_chain_reset_state", "dspi_chain_process_host", "dspi_chain_process_device", "dspi_chain_sync", "dspi_chain_stream",
     "dspi_chain_launch_count", "dspi_delay_samples",
     "dspi_crossfeed_compute_coefficients_f32", "dspi_leveller_compute_coefficients", "dspi_loudness_compute_table_f32", "dspi_host_volume",
+    "dspi_chainq_create", "dspi_chainq_destroy", "dspi_chainq_set_params", "dspi_chainq_upload_biquads", "dspi_chainq_download_biquads",
+    "dspi_chainq_reset_state", "dspi_chainq_process_host", "dspi_chainq_process_device", "dspi_chainq_sync", "dspi_chainq_launch_count",
+    "dspi_crossfeed_compute_coefficients_q28", "dspi_loudness_compute_table_q28",
 ]
 
 
@@ -86,6 +89,19 @@ def lib():
         h.dspi_chain_launch_count.restype = C.c_uint64
         h.dspi_delay_samples.argtypes = [C.c_float, C.c_float, C.c_int]
         h.dspi_delay_samples.restype = C.c_int32
+        h.dspi_chainq_create.argtypes = [C.POINTER(vp), C.POINTER(_ChainDesc)]
+        h.dspi_chainq_destroy.argtypes = [vp]
+        h.dspi_chainq_set_params.argtypes = [vp, u32, u32, vp]
+        h.dspi_chainq_upload_biquads.argtypes = [vp, u32, u32, vp]
+        h.dspi_chainq_download_biquads.argtypes = [vp, u32, u32, vp]
+        h.dspi_chainq_reset_state.argtypes = [vp]
+        h.dspi_chainq_process_host.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
+        h.dspi_chainq_process_device.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
+        h.dspi_chainq_sync.argtypes = [vp]
+        h.dspi_chainq_launch_count.argtypes = [vp]
+        h.dspi_chainq_launch_count.restype = C.c_uint64
+        h.dspi_crossfeed_compute_coefficients_q28.argtypes = [vp, vp, C.c_float]
+        h.dspi_loudness_compute_table_q28.argtypes = [vp, C.c_float, C.c_float, C.c_float]
         h.dspi_crossfeed_compute_coefficients_f32.argtypes = [vp, vp, C.c_float]
         h.dspi_leveller_compute_coefficients.argtypes = [vp, vp, C.c_float]
         h.dspi_loudness_compute_table_f32.argtypes = [vp, C.c_float, C.c_float, C.c_float]
@@ -311,3 +327,80 @@ def host_volume(volume_8_8):
     idx = C.c_uint8()
     v = lib().dspi_host_volume(int(volume_8_8), C.byref(idx))
     return int(v), int(idx.value)
+
+
+class ChainEngineQ28:
+    """Many independent RP2040-shape instances (2 in -> 5 out), Q28 arithmetic (``dspi_chainq_*``)."""
+
+    def __init__(self, n_instances, max_frames, n_bands=L.NUM_BANDS, device=0):
+        self.n_instances, self.max_frames, self.device = int(n_instances), int(max_frames), int(device)
+        self._h = C.c_void_p()
+        desc = _ChainDesc(ARITH_Q28, self.n_instances, int(n_bands), self.device, self.max_frames)
+        _check(lib().dspi_chainq_create(C.byref(self._h), C.byref(desc)))
+
+    def close(self):
+        if self._h:
+            lib().dspi_chainq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params, inst0=0):
+        p = np.ascontiguousarray(params)
+        assert p.dtype == L.CHAIN_PARAMS_Q28 and p.ndim == 1
+        _check(lib().dspi_chainq_set_params(self._h, inst0, p.shape[0], p.ctypes.data))
+
+    def upload_biquads(self, biquads, inst0=0):
+        b = np.ascontiguousarray(biquads)
+        assert b.dtype == L.BIQUAD_Q28 and b.shape[1:] == (L.CHAINQ_EQ_CHANNELS, L.MAX_BANDS)
+        _check(lib().dspi_chainq_upload_biquads(self._h, inst0, b.shape[0], b.ctypes.data))
+
+    def download_biquads(self, n=None, inst0=0):
+        n = self.n_instances - inst0 if n is None else n
+        out = np.zeros((n, L.CHAINQ_EQ_CHANNELS, L.MAX_BANDS), L.BIQUAD_Q28)
+        _check(lib().dspi_chainq_download_biquads(self._h, inst0, n, out.ctypes.data))
+        return out
+
+    def reset_state(self):
+        _check(lib().dspi_chainq_reset_state(self._h))
+
+    def process_host(self, pcm, bit_depth, n_packets, frames_per_packet):
+        F = n_packets * frames_per_packet
+        pcm = np.ascontiguousarray(pcm)
+        assert pcm.dtype == np.uint8 and pcm.shape == (self.n_instances, F * (6 if bit_depth == 24 else 4))
+        spdif = np.zeros((self.n_instances, 2, F, 2), np.int32)
+        pdm = np.zeros((self.n_instances, F, 8), np.uint32)
+        status = np.zeros(self.n_instances, L.STATUS_Q28)
+        _check(lib().dspi_chainq_process_host(self._h, pcm.ctypes.data, bit_depth, n_packets, frames_per_packet,
+                                              spdif.ctypes.data, pdm.ctypes.data, status.ctypes.data))
+        return spdif, pdm, status
+
+    def process_device(self, pcm_ptr, bit_depth, n_packets, frames_per_packet, spdif_ptr=0, pdm_ptr=0, status_ptr=0):
+        _check(lib().dspi_chainq_process_device(self._h, C.c_void_p(int(pcm_ptr)), bit_depth, n_packets, frames_per_packet,
+                                                C.c_void_p(int(spdif_ptr)) if spdif_ptr else None,
+                                                C.c_void_p(int(pdm_ptr)) if pdm_ptr else None,
+                                                C.c_void_p(int(status_ptr)) if status_ptr else None))
+
+    def sync(self):
+        _check(lib().dspi_chainq_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(lib().dspi_chainq_launch_count(self._h))
+
+
+def crossfeed_coefficients_q28(fs, enabled=True, itd=True, preset=0, custom_fc=700.0, custom_feed_db=4.5):
+    st = np.zeros(1, L.XFEED_Q28)
+    cfg = _XfeedCfg(int(enabled), int(itd), int(preset), custom_fc, custom_feed_db)
+    lib().dspi_crossfeed_compute_coefficients_q28(st.ctypes.data, C.byref(cfg), fs)
+    return st[0]
+
+
+def loudness_table_q28(fs, ref_spl=83.0, intensity_pct=100.0):
+    t = np.zeros((L.LOUD_STEPS, 2), L.LOUD_Q28)
+    lib().dspi_loudness_compute_table_q28(t.ctypes.data, ref_spl, intensity_pct, fs)
+    return t

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdspi_b200.so")
-CU_SOURCES = ["engine.cu", "eq_f32.cu", "eq_q28.cu", "chain_f32.cu"]
+CU_SOURCES = ["engine.cu", "eq_f32.cu", "eq_q28.cu", "chain_f32.cu", "chain_q28.cu"]
 C_SOURCES = ["host_params.c"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "eq_core.cuh"
+#include "chain_pdm.cuh"
 
 namespace dspi {
 namespace {
@@ -444,7 +445,7 @@ chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// delta-sigma PDM, pdm_generator.c:351-397 (steady state) + :62-108
+// delta-sigma PDM (chain_pdm.cuh): one instance per lane
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 chain_pdm_kernel(ChainDev d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
@@ -452,52 +453,7 @@ chain_pdm_kernel(ChainDev d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint3
     const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= d.N) return;
     if (!(d.flags[inst] & F_SUB_ON)) return;                                 // usb_audio.c:944
-    const uint32_t Np = d.N_pad;
-    int32_t err1 = d.pdm[0 * Np + inst], err2 = d.pdm[1 * Np + inst];
-    int32_t x1 = d.pdm[2 * Np + inst], x2 = d.pdm[3 * Np + inst], y1 = d.pdm[4 * Np + inst], y2 = d.pdm[5 * Np + inst];
-    int32_t err_acc = d.pdm[6 * Np + inst];
-    uint32_t rng = (uint32_t)d.pdm[7 * Np + inst], fade = (uint32_t)d.pdm[8 * Np + inst];
-    for (uint32_t f = f_begin; f < f_end; f++) {
-        int32_t pcm = d.subq[(size_t)f * Np + inst] >> 14;                   // :352
-        pcm = max(-29500, min(29500, pcm));                                  // :353-354
-        if (fade < 1024u) { pcm = (pcm * (int32_t)fade) >> 10; fade++; }     // :357-360
-        const int32_t target = pcm + 32768;
-        uint32_t words[8];
-#pragma unroll
-        for (int chunk = 0; chunk < 8; chunk++) {
-            rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;             // :63-68
-            const int32_t raw = (int32_t)(rng & 0x1FFu) - 255;               // :368
-            err_acc = ((err_acc * 248) >> 8) + ((err2 >> 8) >> 6);           // :92
-            const int32_t in = raw - err_acc;
-            const int32_t dither = (15778 * in - 31556 * x1 + 15778 * x2 + 31531 * y1 - 15580 * y2) >> 14;   // :98-99
-            x2 = x1; x1 = in; y2 = y1; y1 = dither;
-            // :372-378, re-associated so that only three dependent integer ops separate two decisions:
-            //   s = err2 + dither (the comparator input), m = s >> 31 (all ones when the bit is 0),
-            //   -fb = ~m & -65535;  err1 += target - fb;  s += err1 - fb   (== err2' + dither)
-            uint32_t word = 0;
-            int32_t s = err2 + dither;
-#pragma unroll
-            for (int k = 0; k < 32; k++) {
-                const int32_t m = s >> 31;
-                const int32_t nfb = ~m & -65535;
-                word = __funnelshift_l((uint32_t)~m, word, 1);               // (word << 1) | bit, MSB first
-                err1 += target + nfb;
-                s += err1 + nfb;
-            }
-            err2 = s - dither;
-            words[chunk] = word;
-        }
-        err1 -= err1 >> 16;                                                  // :396-397
-        err2 -= err2 >> 16;
-        if (pdm_out) {
-            uint4 *dst = reinterpret_cast<uint4 *>(pdm_out + ((size_t)inst * F + f) * 8);
-            dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
-            dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
-        }
-    }
-    d.pdm[0 * Np + inst] = err1; d.pdm[1 * Np + inst] = err2;
-    d.pdm[2 * Np + inst] = x1; d.pdm[3 * Np + inst] = x2; d.pdm[4 * Np + inst] = y1; d.pdm[5 * Np + inst] = y2;
-    d.pdm[6 * Np + inst] = err_acc; d.pdm[7 * Np + inst] = (int32_t)rng; d.pdm[8 * Np + inst] = (int32_t)fade;
+    pdm_modulate_frames(d.pdm, d.subq, d.N_pad, inst, f_begin, f_end, F, pdm_out);
 }
 
 // filters[][] of n instances (instance-major AoS) -> packed store with channel = role * N_pad + inst

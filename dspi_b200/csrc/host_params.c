@@ -319,3 +319,70 @@ int16_t dspi_host_volume(int16_t volume_8_8, uint8_t *table_index)
     if (table_index) *table_index = idx;
     return (int16_t)q15[idx];                                               /* stored in an int16_t: 0 dB -> -32768 */
 }
+
+/* ---- Q28 stores (RP2040 build of the same parameter functions) -------------------------------- */
+
+void dspi_crossfeed_compute_coefficients_q28(dspi_crossfeed_state_q28 *st, const dspi_crossfeed_config *cfg, float fs)
+{
+    dspi_crossfeed_state_f32 f;
+    dspi_crossfeed_compute_coefficients_f32(&f, cfg, fs);                   /* same float maths, crossfeed.c:35-109 */
+    memset(st, 0, sizeof(*st));
+    if (!cfg->enabled || fs < 1.0f) return;
+    st->lp_a0 = to_q28(f.lp_a0);                                            /* :116-119 (int32_t)(x * 2^28) */
+    st->lp_b1 = to_q28(f.lp_b1);
+    st->ap_a = to_q28(f.ap_a);
+}
+
+static void shelf_rbj_q28(float freq, float Q, float gain_db, int high, float fs, dspi_loudness_coeffs_q28 *o)   /* loudness.c:85-162 */
+{
+    if (fabsf(gain_db) < 0.01f) {
+        memset(o, 0, sizeof(*o));
+        o->bypass = 1;
+        o->b0 = 1 << 28;
+        return;
+    }
+    o->bypass = 0;
+    const float A = powf(10.0f, gain_db / 40.0f);
+    const float omega = 2.0f * PI_F * freq / fs;
+    const float sn = sinf(omega), cs = cosf(omega);
+    const float alpha = sn / (2.0f * Q);
+    const float rootA = sqrtf(A);
+    float n0, n1, n2, d0, d1, d2;
+    if (high) {
+        n0 = A * ((A + 1) + (A - 1) * cs + 2 * rootA * alpha);
+        n1 = -2 * A * ((A - 1) + (A + 1) * cs);
+        n2 = A * ((A + 1) + (A - 1) * cs - 2 * rootA * alpha);
+        d0 = (A + 1) - (A - 1) * cs + 2 * rootA * alpha;
+        d1 = 2 * ((A - 1) - (A + 1) * cs);
+        d2 = (A + 1) - (A - 1) * cs - 2 * rootA * alpha;
+    } else {
+        n0 = A * ((A + 1) - (A - 1) * cs + 2 * rootA * alpha);
+        n1 = 2 * A * ((A - 1) - (A + 1) * cs);
+        n2 = A * ((A + 1) - (A - 1) * cs - 2 * rootA * alpha);
+        d0 = (A + 1) + (A - 1) * cs + 2 * rootA * alpha;
+        d1 = -2 * ((A - 1) + (A + 1) * cs);
+        d2 = (A + 1) + (A - 1) * cs - 2 * rootA * alpha;
+    }
+    o->b0 = to_q28(n0 / d0);
+    o->b1 = to_q28(n1 / d0);
+    o->b2 = to_q28(n2 / d0);
+    o->a1 = to_q28(d1 / d0);
+    o->a2 = to_q28(d2 / d0);
+}
+
+void dspi_loudness_compute_table_q28(dspi_loudness_coeffs_q28 table[61][2], float ref_spl, float intensity_pct, float fs)
+{
+    if (fs < 1.0f) fs = 48000.0f;
+    if (ref_spl < 40.0f) ref_spl = 40.0f;
+    if (ref_spl > 100.0f) ref_spl = 100.0f;
+    memset(table, 0, sizeof(dspi_loudness_coeffs_q28) * 61 * 2);
+    for (int step = 0; step < 61; step++) {
+        float phon = ref_spl + (float)(step - 60);
+        if (phon < 20.0f) phon = 20.0f;
+        if (phon > ref_spl) phon = ref_spl;
+        const float low_db = shelf_gain_db(44.0f, 0.432f, 80.4f, ref_spl, phon, intensity_pct);
+        const float high_db = shelf_gain_db(13.9f, 0.301f, 17.8f, ref_spl, phon, intensity_pct);
+        shelf_rbj_q28(200.0f, 0.707f, low_db, 0, fs, &table[step][0]);
+        shelf_rbj_q28(6000.0f, 0.707f, high_db, 1, fs, &table[step][1]);
+    }
+}

@@ -103,3 +103,17 @@ CHAIN_PARAMS_F32 = np.dtype({
     "offsets": [0, 1, 2, 3, 4, 5, 8, 12, 16, 20, 28, 84, 112, 148],
     "itemsize": 544})
 assert MATRIX_MIXER_F32.itemsize == 396 and STATUS.itemsize == 26 and CHAIN_PARAMS_F32.itemsize == 544
+
+# ---- Q28 chain records (RP2040 shape: 2 in -> 5 out) --------------------------------------------
+CHAINQ_OUTPUTS = 5
+CHAINQ_EQ_CHANNELS = 7
+CHAINQ_MAX_DELAY = 2048
+MATRIX_MIXER_Q28 = np.dtype([("crosspoints", CROSSPOINT, (2, CHAINQ_OUTPUTS)), ("outputs", OUTPUT, (CHAINQ_OUTPUTS,))])
+STATUS_Q28 = np.dtype([("peaks", np.uint16, (CHAINQ_EQ_CHANNELS,)), ("cpu0_load", _b), ("cpu1_load", _b), ("clip_flags", np.uint16)])
+CHAIN_PARAMS_Q28 = np.dtype({
+    "names": ["bypass_master_eq", "loudness_enabled", "crossfeed_enabled", "leveller_enabled", "host_mute", "leveller_lookahead",
+              "host_vol_mul", "preset_mute_gain", "master_volume_q15", "preamp_q28", "loudness", "crossfeed", "leveller", "matrix"],
+    "formats": [_b, _b, _b, _b, _b, _b, np.int16, _f, _i, (_i, (2,)), (LOUD_Q28, (2,)), XFEED_Q28, LEV_COEFFS, MATRIX_MIXER_Q28],
+    "offsets": [0, 1, 2, 3, 4, 5, 8, 12, 16, 20, 28, 76, 104, 140],
+    "itemsize": 360})
+assert MATRIX_MIXER_Q28.itemsize == 220 and STATUS_Q28.itemsize == 18 and CHAIN_PARAMS_Q28.itemsize == 360

@@ -254,6 +254,65 @@ uint64_t dspi_chain_launch_count(dspi_chain *c);
 /* dsp_update_delay_samples() for one output, dsp_pipeline.c:216-239 (is_last adds SUB_ALIGN_SAMPLES) */
 int32_t dspi_delay_samples(float delay_ms, float sample_rate, int is_last);
 
+/* ---- full signal chain, RP2040 arithmetic (Q28 fixed point, 2 in -> 5 out) ---------------------- */
+/* process_audio_packet(), usb_audio.c:968-1283 (single-core branch :1191-1276): every stage in
+ * 32-bit wrapping Q28/Q15 arithmetic (fast_mul_q28 dsp_pipeline.c:47-58, fast_mul_q15
+ * config.h:556-567), crossfeed.c:161-180, leveller.c:275-389; bit-exact. */
+#define DSPI_CHAINQ_OUTPUTS      5    /* config.h:326                                               */
+#define DSPI_CHAINQ_EQ_CHANNELS  7    /* config.h:327                                               */
+#define DSPI_CHAINQ_MAX_DELAY 2048    /* config.h:86                                                */
+
+/* LoudnessCoeffs (RP2040), loudness.h:21 (24 bytes); CrossfeedState (RP2040), crossfeed.h:53-58 */
+typedef struct { int32_t b0, b1, b2, a1, a2; uint8_t bypass; } dspi_loudness_coeffs_q28;
+typedef struct { int32_t lp_a0, lp_b1, lp_state_L, lp_state_R, ap_a, ap_state_L, ap_state_R; } dspi_crossfeed_state_q28;
+/* MatrixMixer (RP2040), config.h:403-406 (220 bytes); SystemStatusPacket (RP2040, 18 bytes) */
+typedef struct {
+    dspi_matrix_crosspoint crosspoints[2][DSPI_CHAINQ_OUTPUTS];
+    dspi_output_channel outputs[DSPI_CHAINQ_OUTPUTS];
+} dspi_matrix_mixer_q28;
+typedef struct { uint16_t peaks[DSPI_CHAINQ_EQ_CHANNELS]; uint8_t cpu0_load, cpu1_load; uint16_t clip_flags; } dspi_status_q28;
+
+typedef struct {
+    uint8_t bypass_master_eq, loudness_enabled, crossfeed_enabled, leveller_enabled;
+    uint8_t host_mute, leveller_lookahead, reserved0[2];
+    int16_t host_vol_mul;            /* audio_state.vol_mul (int16: 0 dB gives -32768)              */
+    int16_t reserved1;
+    float preset_mute_gain;          /* quantised to Q15 per packet, usb_audio.c:976-978            */
+    int32_t master_volume_q15;       /* usb_audio.c:162                                             */
+    int32_t preamp_q28[2];           /* global_preamp_mul[]                                         */
+    dspi_loudness_coeffs_q28 loudness[2];
+    dspi_crossfeed_state_q28 crossfeed;
+    dspi_leveller_coeffs leveller;
+    dspi_matrix_mixer_q28 matrix;
+} dspi_chain_params_q28;
+
+#ifdef __cplusplus
+static_assert(sizeof(dspi_loudness_coeffs_q28) == 24 && sizeof(dspi_crossfeed_state_q28) == 28 && sizeof(dspi_matrix_mixer_q28) == 220 &&
+              sizeof(dspi_status_q28) == 18, "reference layouts");
+#else
+_Static_assert(sizeof(dspi_loudness_coeffs_q28) == 24 && sizeof(dspi_crossfeed_state_q28) == 28 && sizeof(dspi_matrix_mixer_q28) == 220 &&
+               sizeof(dspi_status_q28) == 18, "reference layouts");
+#endif
+
+typedef struct dspi_chainq dspi_chainq;
+int dspi_chainq_create(dspi_chainq **out, const dspi_chain_desc *desc);      /* desc->arith must be DSPI_ARITH_Q28 */
+int dspi_chainq_destroy(dspi_chainq *c);
+int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dspi_chain_params_q28 *params);
+/* filters[7][12] per instance: biquads[n][7][12] (master L, R, Out1..4, sub) */
+int dspi_chainq_upload_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, const dspi_biquad_q28 *biquads);
+int dspi_chainq_download_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_biquad_q28 *biquads);
+int dspi_chainq_reset_state(dspi_chainq *c);
+/* pcm as for dspi_chain_process_host; spdif_out [n_instances][2][n_frames][2]; pdm_out [n_instances][n_frames][8] */
+int dspi_chainq_process_host(dspi_chainq *c, const void *pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t frames_per_packet,
+                             int32_t *spdif_out, uint32_t *pdm_out, dspi_status_q28 *status);
+int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t frames_per_packet,
+                               int32_t *d_spdif_out, uint32_t *d_pdm_out, dspi_status_q28 *d_status);
+int dspi_chainq_sync(dspi_chainq *c);
+uint64_t dspi_chainq_launch_count(dspi_chainq *c);
+/* Q28 stores of the crossfeed and loudness parameter functions (crossfeed.c:116-119, loudness.c:131-162) */
+void dspi_crossfeed_compute_coefficients_q28(dspi_crossfeed_state_q28 *st, const dspi_crossfeed_config *cfg, float sample_rate);
+void dspi_loudness_compute_table_q28(dspi_loudness_coeffs_q28 table[61][2], float ref_spl, float intensity_pct, float sample_rate);
+
 /* pinned host memory helpers */
 void *dspi_host_alloc(size_t bytes);
 void dspi_host_free(void *p);

@@ -86,3 +86,51 @@ def pcm_bytes(N, F, bit_depth, seed):
     b[..., 1] = (s >> 8) & 0xFF
     b[..., 2] = (s >> 16) & 0xFF
     return b.reshape(N, F * 6)
+
+
+def chain_params_q28(oracle, N, fs, seed, leveller=True):
+    """CHAIN_PARAMS_Q28 [N] + BIQUAD_Q28 [N, 7, 12] (RP2040 shape), every stage exercised."""
+    rng = np.random.default_rng(seed)
+    P = np.zeros(N, L.CHAIN_PARAMS_Q28)
+    loud_tab = api.loudness_table_q28(fs, 83.0, 100.0)
+    for i in range(N):
+        p = P[i]
+        u = rng.random(16)
+        vol_mul, row = api.host_volume(int(-40 * 256 * u[0]))
+        p["host_vol_mul"] = vol_mul
+        p["host_mute"] = 1 if u[1] < 0.05 else 0
+        p["preset_mute_gain"] = 1.0 if u[1] > 0.3 else np.float32(u[1] * 3)
+        p["master_volume_q15"] = int(10.0 ** (-6.0 * u[2] / 20.0) * 32768.0)
+        p["preamp_q28"] = [int(10.0 ** ((-3 + 6 * u[3]) / 20.0) * (1 << 28)), int(10.0 ** ((-3 + 6 * u[4]) / 20.0) * (1 << 28))]
+        p["bypass_master_eq"] = 1 if u[5] < 0.15 else 0
+        p["loudness_enabled"] = 1 if u[6] < 0.7 else 0
+        p["loudness"] = loud_tab[row]
+        p["crossfeed"] = api.crossfeed_coefficients_q28(fs, True, u[7] < 0.8, int(u[8] * 4) % 4, 500 + 1500 * u[9], 15 * u[10])
+        p["crossfeed_enabled"] = 1 if u[11] < 0.7 else 0
+        p["leveller"] = api.leveller_coefficients(fs, 100 * u[12], int(u[13] * 3) % 3, 15.0, -96.0)
+        p["leveller_enabled"] = 1 if (leveller and u[14] < 0.6) else 0
+        p["leveller_lookahead"] = 1 if u[15] < 0.5 else 0
+        m = p["matrix"]
+        v = rng.random((5, 8))
+        for o in range(5):
+            oc = m["outputs"][o]
+            oc["enabled"] = 1 if v[o, 0] < 0.85 else 0
+            oc["mute"] = 1 if v[o, 1] < 0.1 else 0
+            oc["gain_db"] = np.float32(-6 * v[o, 2])
+            oc["gain_linear"] = np.float32(10.0 ** (float(oc["gain_db"]) / 20.0))
+            oc["delay_ms"] = np.float32(20.0 * v[o, 3]) if v[o, 4] < 0.7 else np.float32(0.0)
+            ds = oracle.lib.orc_delay_samples(float(oc["delay_ms"]), fs, 1 if o == 4 else 0, 2048)
+            oc["delay_samples"] = ds
+            for side in range(2):
+                x = m["crosspoints"][side, o]
+                x["enabled"] = 1 if ((o == 4) or (o % 2 == side) or v[o, 5 + side] < 0.2) else 0
+                x["phase_invert"] = 1 if (v[o, 7] < 0.2 and side == 1) else 0
+                x["gain_db"] = np.float32(-6.0 if o == 4 else 0.0)
+                x["gain_linear"] = np.float32(0.5 if o == 4 else 1.0)
+    bq = np.zeros((N, L.CHAINQ_EQ_CHANNELS, L.MAX_BANDS), L.BIQUAD_Q28)
+    for i in range(N):
+        variant = "mixed" if i % 3 == 0 else ("A" if i % 3 == 1 else "B")
+        bq[i] = api.compute_coefficients(W.eq_params(variant, L.CHAINQ_EQ_CHANNELS, fs=fs, seed=seed + i), q28=True, fs=fs)
+        if i % 7 == 3:
+            bq[i, 4]["bypass"] = 1
+    return P, bq

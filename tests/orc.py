@@ -284,3 +284,87 @@ def orc_chain_run(oracle, flavour, chain, pcm_bytes, bit_depth, n_packets, fpp):
         fn(C.addressof(chain), data.ctypes.data + p * fpp * bpf, fpp * bpf, bit_depth,
            spdif.ctypes.data + p * fpp * 8, F * 2, pdm.ctypes.data + p * fpp * 32)
     return spdif, pdm
+
+
+class OrcBiquadQ28(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("b0", "b1", "b2", "a1", "a2", "s1", "s2")] + [("bypass", C.c_uint8)]
+
+
+class OrcLoudQ28(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("b0", "b1", "b2", "a1", "a2")] + [("bypass", C.c_uint8)]
+
+
+class OrcXfeedQ28(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("lp_a0", "lp_b1", "lp_state_L", "lp_state_R", "ap_a", "ap_state_L", "ap_state_R")]
+
+
+class OrcLevStateQ28(C.Structure):
+    _fields_ = [("env_sq_l", C.c_int32), ("env_sq_r", C.c_int32), ("gain_smooth_db", C.c_float), ("gain_q28", C.c_int32),
+                ("gain_prev_q28", C.c_int32), ("lookahead_buf", (C.c_int32 * 480) * 2), ("la_write_idx", C.c_uint32)]
+
+
+class OrcChainQ28(C.Structure):
+    _fields_ = [("n_out", C.c_uint32), ("n_bands", C.c_uint32), ("max_delay", C.c_uint32),
+                ("bypass_master_eq", C.c_uint8), ("loudness_on", C.c_uint8), ("crossfeed_on", C.c_uint8), ("leveller_on", C.c_uint8),
+                ("host_mute", C.c_uint8), ("any_delay_active", C.c_uint8), ("lev_lookahead", C.c_uint8), ("pad0", C.c_uint8),
+                ("host_vol_mul", C.c_int16), ("pad1", C.c_int16), ("preset_mute_gain", C.c_float), ("master_volume_q15", C.c_int32),
+                ("preamp_q28", C.c_int32 * 2), ("xp", (OrcCrosspoint * 9) * 2), ("out", OrcOutput * 9), ("delay_samples", C.c_int32 * 9),
+                ("channel_bypassed", C.c_uint8 * 11), ("pad2", C.c_uint8), ("filters", (OrcBiquadQ28 * 12) * 11), ("loud", OrcLoudQ28 * 2),
+                ("loud_state", (OrcBiquadQ28 * 2) * 2), ("xfeed", OrcXfeedQ28), ("levc", OrcLevCoeffs), ("levs", OrcLevStateQ28),
+                ("delay_lines", (C.c_int32 * 4096) * 9), ("delay_widx", C.c_uint32), ("pdm", OrcPdm), ("peaks", C.c_uint16 * 11),
+                ("clip_flags", C.c_uint16)]
+
+
+def make_orc_chain_q28(oracle, params, biquads):
+    """orc_chain_q28 for one instance from a CHAIN_PARAMS_Q28 record and its [7, 12] biquads."""
+    assert C.sizeof(OrcChainQ28) == oracle.lib.orc_sizeof(3)
+    c = OrcChainQ28()
+    c.n_out, c.n_bands, c.max_delay = 5, 10, 2048
+    c.bypass_master_eq = int(params["bypass_master_eq"])
+    c.loudness_on = int(params["loudness_enabled"])
+    c.crossfeed_on = int(params["crossfeed_enabled"])
+    c.leveller_on = int(params["leveller_enabled"])
+    c.host_mute = int(params["host_mute"])
+    c.lev_lookahead = int(params["leveller_lookahead"])
+    c.host_vol_mul = int(params["host_vol_mul"])
+    c.preset_mute_gain = float(params["preset_mute_gain"])
+    c.master_volume_q15 = int(params["master_volume_q15"])
+    c.preamp_q28[0], c.preamp_q28[1] = int(params["preamp_q28"][0]), int(params["preamp_q28"][1])
+    m = params["matrix"]
+    any_delay = False
+    for o in range(5):
+        for i in range(2):
+            x = m["crosspoints"][i, o]
+            c.xp[i][o].enabled, c.xp[i][o].phase_invert = int(x["enabled"]), int(x["phase_invert"])
+            c.xp[i][o].gain_db, c.xp[i][o].gain_linear = float(x["gain_db"]), float(x["gain_linear"])
+        oc = m["outputs"][o]
+        c.out[o].enabled, c.out[o].mute = int(oc["enabled"]), int(oc["mute"])
+        c.out[o].gain_db, c.out[o].gain_linear = float(oc["gain_db"]), float(oc["gain_linear"])
+        c.out[o].delay_ms, c.out[o].delay_samples = float(oc["delay_ms"]), int(oc["delay_samples"])
+        c.delay_samples[o] = int(oc["delay_samples"])
+        any_delay = any_delay or int(oc["delay_samples"]) > 0
+    c.any_delay_active = 1 if any_delay else 0
+    bq = np.ascontiguousarray(biquads)
+    for r in range(7):
+        C.memmove(C.addressof(c.filters[r]), bq[r].ctypes.data, 12 * 32)
+        c.channel_bypassed[r] = 1 if all(int(biquads[r, b]["bypass"]) for b in range(10)) else 0
+    for j in range(2):
+        C.memmove(C.addressof(c.loud[j]), params["loudness"][j:j + 1].tobytes(), 24)
+    C.memmove(C.addressof(c.xfeed), params["crossfeed"].tobytes(), 28)
+    C.memmove(C.addressof(c.levc), params["leveller"].tobytes(), 36)
+    c.levs.gain_q28 = 1 << 28
+    c.levs.gain_prev_q28 = 1 << 28
+    c.pdm.rng = 123456789
+    return c
+
+
+def orc_chain_run_q28(oracle, chain, pcm_bytes, bit_depth, n_packets, fpp):
+    F = n_packets * fpp
+    bpf = 6 if bit_depth == 24 else 4
+    spdif = np.zeros((2, F, 2), np.int32)
+    pdm = np.zeros((F, 8), np.uint32)
+    data = np.ascontiguousarray(pcm_bytes)
+    for p in range(n_packets):
+        oracle.lib.orc_q28_chain_packet(C.addressof(chain), data.ctypes.data + p * fpp * bpf, fpp * bpf, bit_depth,
+                                        spdif.ctypes.data + p * fpp * 8, F * 2, pdm.ctypes.data + p * fpp * 32)
+    return spdif, pdm

@@ -118,3 +118,17 @@ def test_chain_parameter_functions_match_the_reference(lib, oracle, refs):
         for fs in (48000.0, 96000.0):
             for last in (0, 1):
                 assert api.delay_samples(ms, fs, last) == refs["f32s"].lib.ref_delay_samples(ms, fs, last)
+
+
+def test_q28_chain_parameter_functions_match_the_reference(lib, refs):
+    from tests.util import field_bits
+    for fs in (48000.0, 96000.0):
+        for preset in range(4):
+            mine = api.crossfeed_coefficients_q28(fs, True, 1, preset, 1234.0, 7.0)
+            st = np.zeros(1, L.XFEED_Q28)
+            refs["q28"].lib.ref_xfeed_coeffs(st.ctypes.data, 1, 1, preset, 1234.0, 7.0, fs)
+            assert np.array_equal(field_bits(np.array([mine])), field_bits(st))
+        for ref_spl, inten in ((83.0, 100.0), (60.0, 35.0)):
+            want = np.zeros((L.LOUD_STEPS, 2), L.LOUD_Q28)
+            refs["q28"].lib.ref_loud_table(want.ctypes.data, ref_spl, inten, fs)
+            assert np.array_equal(field_bits(api.loudness_table_q28(fs, ref_spl, inten)), field_bits(want))
