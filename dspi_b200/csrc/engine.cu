@@ -67,6 +67,8 @@ struct dspi_eq {
     void *d_aos;             // Biquad[c_pad][12] in the reference layout (device mirror)
     void *d_coef;            // packed coefficient + state store
     uint64_t *d_modes;       // float only
+    uint32_t *d_sched;       // float only: dynamic scheduler words
+    int n_sms;
     size_t aos_elem;
     uint64_t launches;
     // host-path staging
@@ -149,6 +151,8 @@ int dspi_eq_create(dspi_eq **out, const dspi_eq_desc *desc)
     if ((err = cudaMemsetAsync(e->d_coef, 0, coef_bytes, e->stream)) != cudaSuccess) goto cuda_fail;
     if (!q28) {
         if ((err = cudaMalloc(&e->d_modes, (size_t)e->c_pad * 8)) != cudaSuccess) goto cuda_fail;
+        if ((err = cudaMalloc(&e->d_sched, (size_t)(1 + e->n_groups) * 4)) != cudaSuccess) goto cuda_fail;
+        if ((err = cudaDeviceGetAttribute(&e->n_sms, cudaDevAttrMultiProcessorCount, desc->device)) != cudaSuccess) goto cuda_fail;
         if ((err = cudaMemsetAsync(e->d_modes, 0, (size_t)e->c_pad * 8, e->stream)) != cudaSuccess) goto cuda_fail;
     }
     // every band of every (padding) channel starts bypassed, like dsp_init_default_filters() (dsp_pipeline.c:177-199)
@@ -178,6 +182,7 @@ int dspi_eq_destroy(dspi_eq *e)
     if (e->d_aos) cudaFree(e->d_aos);
     if (e->d_coef) cudaFree(e->d_coef);
     if (e->d_modes) cudaFree(e->d_modes);
+    if (e->d_sched) cudaFree(e->d_sched);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
@@ -278,6 +283,8 @@ static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint3
                  : (void *)((float *)e->d_coef + (size_t)g0 * DSPI_MAX_BANDS * 8 * 32 * e->cpl);
     a.modes = e->d_modes ? e->d_modes + (size_t)g0 * e->rows : nullptr;
     a.n_groups = ng;
+    a.sched = e->d_sched;
+    a.n_sms = e->n_sms;
     a.n_rows = n_rows;
     a.T = T;
     a.n_bands = e->desc.n_bands;

@@ -228,6 +228,12 @@ __device__ __noinline__ float2 slow_band(float *xs, int n, uint32_t mode, float 
 // ---------------------------------------------------------------------------------------
 // lane <-> register-tile plumbing
 // ---------------------------------------------------------------------------------------
+// L2-coherent accesses (bypass the per-SM L1) for words another SM may have written in this launch
+__device__ __forceinline__ float ld_cg(const float *p) { return __ldcg(p); }
+__device__ __forceinline__ P2 ld_cg(const P2 *p) { P2 r; r.v = __ldcg(&p->v); return r; }
+__device__ __forceinline__ void st_cg(float *p, float v) { __stcg(p, v); }
+__device__ __forceinline__ void st_cg(P2 *p, P2 v) { __stcg(&p->v, v.v); }
+
 template <typename V> struct Lanes;
 template <> struct Lanes<float> {
     static constexpr int CPL = 1;
@@ -257,15 +263,22 @@ struct EqBank {
     uint32_t nb_active;
     bool all_tdf2;
 
-    __device__ __forceinline__ void load(const V *base, const uint64_t *const (&mode_ptr)[CPL], uint32_t nb)
+    // `shared_state`: the state words may have been written by another SM during this launch
+    // (dynamic time slices): read them past the non-coherent L1
+    __device__ __forceinline__ void load(const V *base, const uint64_t *const (&mode_ptr)[CPL], uint32_t nb, bool shared_state = false)
     {
         nb_active = nb;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
 #pragma unroll
             for (int k = 0; k < 6; k++) c[b][k] = base[(b * 8 + k) * 32];
-            st[b][0] = base[(b * 8 + 6) * 32];
-            st[b][1] = base[(b * 8 + 7) * 32];
+            if (shared_state) {
+                st[b][0] = ld_cg(base + (b * 8 + 6) * 32);
+                st[b][1] = ld_cg(base + (b * 8 + 7) * 32);
+            } else {
+                st[b][0] = base[(b * 8 + 6) * 32];
+                st[b][1] = base[(b * 8 + 7) * 32];
+            }
         }
 #pragma unroll
         for (int h = 0; h < CPL; h++) {
@@ -290,12 +303,17 @@ struct EqBank {
         all_tdf2 = __all_sync(0xffffffffu, mine);
     }
 
-    __device__ __forceinline__ void store(V *base) const
+    __device__ __forceinline__ void store(V *base, bool shared_state = false) const
     {
 #pragma unroll
         for (int b = 0; b < NB; b++) {
-            base[(b * 8 + 6) * 32] = st[b][0];
-            base[(b * 8 + 7) * 32] = st[b][1];
+            if (shared_state) {
+                st_cg(base + (b * 8 + 6) * 32, st[b][0]);
+                st_cg(base + (b * 8 + 7) * 32, st[b][1]);
+            } else {
+                base[(b * 8 + 6) * 32] = st[b][0];
+                base[(b * 8 + 7) * 32] = st[b][1];
+            }
         }
     }
 
