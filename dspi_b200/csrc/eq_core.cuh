@@ -392,22 +392,65 @@ struct EqBank {
         }
     }
 
+    // two consecutive bands of the SAME topology in one pass: band b+1 of sample j only needs band b of
+    // sample j, so inside the unrolled block the scheduler overlaps the two recurrences (a wavefront of
+    // depth 2) and the tile travels through shared memory once instead of twice
+    template <int MODE>
+    __device__ __forceinline__ void band_loop2(V *col, int n, const V (&ca)[6], V &a0, V &a1, const V (&cb)[6], V &b0, V &b1, const V nz)
+    {
+#pragma unroll 2
+        for (int i = 0; i < n; i += 4) {
+            V x[4], y[4], z[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) x[j] = col[(i + j) * 32];
+            if constexpr (MODE == (int)kModeTdf2) {
+                tdf2_tile<FUSED>(x, y, ca, a0, a1, nz);
+                tdf2_tile<FUSED>(y, z, cb, b0, b1, nz);
+            } else {
+                svf_tile<FUSED, MODE>(x, y, ca, a0, a1, nz);
+                svf_tile<FUSED, MODE>(y, z, cb, b0, b1, nz);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) col[(i + j) * 32] = z[j];
+        }
+    }
+
     // Band-outer pass over a shared-memory tile in column layout (the reference's own loop order,
     // dsp_pipeline.c:286-364): topology dispatch happens once per band per tile, each band is a
     // small rolled loop (stays in the instruction cache), samples travel LDS.64 -> registers ->
     // STS.64 between bands.  `col` already includes this lane's offset.
     __device__ __forceinline__ void run_columns(V *col, int n, const V nz)
     {
+        bool fused_prev = false;                                // band b was already processed together with b-1
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             if (b >= (int)nb_active) break;
+            if (fused_prev) { fused_prev = false; continue; }
             const uint32_t m = (uint32_t)(mode_w >> (4 * b)) & 15u;
-            if (((uni >> b) & 1u) && (n & 3) == 0) {
-                if (m == kModeTdf2) band_loop<(int)kModeTdf2>(col, n, c[b], st[b][0], st[b][1], nz);
-                else if (m == kModeSvfPK) band_loop<kMixPK>(col, n, c[b], st[b][0], st[b][1], nz);
-                else if (m == kModeSvfSH) band_loop<kMixSH>(col, n, c[b], st[b][0], st[b][1], nz);
-                else if (m == kModeSvfLP) band_loop<kMixLP>(col, n, c[b], st[b][0], st[b][1], nz);
-                else if (m == kModeSvfHP) band_loop<kMixHP>(col, n, c[b], st[b][0], st[b][1], nz);
+            const bool fast = ((uni >> b) & 1u) && (n & 3) == 0;
+            if (fast) {
+                bool pair = false;
+                if constexpr (true) {
+                    if (b + 1 < NB) {
+                        const uint32_t m1 = (uint32_t)(mode_w >> (4 * (b + 1))) & 15u;
+                        pair = (b + 1 < (int)nb_active) && ((uni >> (b + 1)) & 1u) && m1 == m && m != kModeBypass;
+                    }
+                }
+                if (pair) {
+                    const int b1 = (b + 1 < NB) ? b + 1 : b;         // constant after unrolling
+                    if (m == kModeTdf2) band_loop2<(int)kModeTdf2>(col, n, c[b], st[b][0], st[b][1], c[b1], st[b1][0], st[b1][1], nz);
+                    else if (m == kModeSvfPK) band_loop2<kMixPK>(col, n, c[b], st[b][0], st[b][1], c[b1], st[b1][0], st[b1][1], nz);
+                    else if (m == kModeSvfSH) band_loop2<kMixSH>(col, n, c[b], st[b][0], st[b][1], c[b1], st[b1][0], st[b1][1], nz);
+                    else if (m == kModeSvfLP) band_loop2<kMixLP>(col, n, c[b], st[b][0], st[b][1], c[b1], st[b1][0], st[b1][1], nz);
+                    else band_loop2<kMixHP>(col, n, c[b], st[b][0], st[b][1], c[b1], st[b1][0], st[b1][1], nz);
+                    fused_prev = true;
+                } else {
+                    if (m == kModeTdf2) band_loop<(int)kModeTdf2>(col, n, c[b], st[b][0], st[b][1], nz);
+                    else if (m == kModeSvfPK) band_loop<kMixPK>(col, n, c[b], st[b][0], st[b][1], nz);
+                    else if (m == kModeSvfSH) band_loop<kMixSH>(col, n, c[b], st[b][0], st[b][1], nz);
+                    else if (m == kModeSvfLP) band_loop<kMixLP>(col, n, c[b], st[b][0], st[b][1], nz);
+                    else if (m == kModeSvfHP) band_loop<kMixHP>(col, n, c[b], st[b][0], st[b][1], nz);
+                }
             } else {
                 float ns0[CPL], ns1[CPL];
 #pragma unroll

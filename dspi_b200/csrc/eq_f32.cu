@@ -32,7 +32,7 @@ using namespace core;
 constexpr int kTileT = 32;          // samples per shared-memory tile row: 128 B == swizzle span
 constexpr int kStages = 3;
 
-template <typename V, bool FUSED, int NB>
+template <typename V, bool FUSED, int NB, bool DYN>
 __global__ void __launch_bounds__(256 * 2 / Lanes<V>::CPL, 1)
 eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samples, uint32_t ld, V *__restrict__ coef,
               const uint64_t *__restrict__ modes, uint32_t n_groups, uint32_t n_rows, uint32_t T, uint32_t nb_active, uint32_t use_tma, uint32_t dbg, unsigned long long nz_bits, uint32_t slice_tiles, uint32_t *__restrict__ sched)
@@ -69,12 +69,12 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
     // coefficient store, ordered by a per-group completion counter (release/acquire).  65536
     // channels are 1024 groups for 592 warp schedulers: no static split can load them evenly, the
     // time slices can.
-    const uint32_t n_slices = sched ? (ntiles + slice_tiles - 1) / slice_tiles : 1;
-    const uint32_t n_items = sched ? n_groups * n_slices : 0;
+    const uint32_t n_slices = DYN ? (ntiles + slice_tiles - 1) / slice_tiles : 1;
+    const uint32_t n_items = DYN ? n_groups * n_slices : 0;
     uint32_t tcount = 0;                                        // tiles this warp has pushed through its ring (stage / parity bookkeeping)
     for (;;) {
         uint32_t g, tile_begin, tile_end, slice = 0;
-        if (sched) {
+        if constexpr (DYN) {
             uint32_t item = 0;
             if (lane == 0) item = atomicAdd(&sched[0], 1u);
             item = __shfl_sync(0xffffffffu, item, 0);
@@ -105,7 +105,7 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
             tma_load_2d(my_smem + s * kStageBytes, &tmap, &full[s], tile * kTileT, c0);
         };
         if (use_tma && mem_on && lane == 0) {
-            tma_store_wait_read<0>();                           // ring buffers of the previous item are drained
+            if constexpr (DYN) tma_store_wait_read<0>();        // ring buffers of the previous item are drained
             for (uint32_t j = 0; j + 1 < kStages && tile_begin + j < tile_end; j++) issue_load(tile_begin + j, tcount + j);
         }
 
@@ -116,7 +116,7 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
             const uint64_t *mp[CPL];
 #pragma unroll
             for (int h = 0; h < CPL; h++) mp[h] = modes + (size_t)g * kRows + h * 32 + lane;
-            bank.load(my_coef, mp, nb_active, sched != nullptr);
+            bank.load(my_coef, mp, nb_active, DYN);
         }
 
         // ---- stream the tiles of this item --------------------------------------------------------
@@ -237,8 +237,8 @@ eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samp
         }
 
 
-        bank.store(my_coef, sched != nullptr);                   // filter state back to the coefficient store
-        if (!sched) break;
+        bank.store(my_coef, DYN);                                // filter state back to the coefficient store
+        if constexpr (!DYN) break;
         __threadfence();                                        // state visible before the slice counter moves
         __syncwarp();
         if (lane == 0) atomicExch(&sched[1 + g], slice + 1);
@@ -252,10 +252,12 @@ cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
     constexpr int CPL = Lanes<V>::CPL;
     constexpr int kWarps = 16 / CPL;
     constexpr size_t smem = (size_t)kWarps * kStages * (32 * CPL) * kTileT * 4;
-    auto kern = eq_f32_kernel<V, FUSED, NB>;
+    auto kern = eq_f32_kernel<V, FUSED, NB, false>;
+    auto kern_dyn = eq_f32_kernel<V, FUSED, NB, true>;
     static bool configured = false;                             // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -264,7 +266,10 @@ cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
     uint32_t slice_tiles = 0;
     uint32_t *sched = nullptr;
     const uint32_t ntiles = (a.T + kTileT - 1) / kTileT;
-    if (a.sched && a.use_tma && ntiles >= 32 && !(a.dbg & 8u)) {  // enough time to slice: persistent grid, dynamic items
+    // The dynamic schedule is opt-in (DSPI_DBG=8): measured on B200 it loses ~6 % to the static one at
+    // 65536 channels - a scheduler left with ONE resident warp runs it well below half the two-warp rate,
+    // which eats the balance it buys.
+    if (a.sched && a.use_tma && ntiles >= 32 && (a.dbg & 8u)) {
         slice_tiles = 16;
         sched = a.sched;
         if (grid > (uint32_t)a.n_sms) grid = a.n_sms;
@@ -272,8 +277,12 @@ cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
         cudaError_t e = cudaMemsetAsync(sched, 0, (size_t)(1 + n_groups) * sizeof(uint32_t), stream);
         if (e != cudaSuccess) return e;
     }
-    kern<<<grid, kWarps * 32, smem, stream>>>(a.tmap, (float *)a.samples, a.ld, (V *)a.coef, a.modes, n_groups, a.n_rows, a.T, a.n_bands, a.use_tma, a.dbg,
-                                              0x8000000080000000ull, slice_tiles, sched);
+    if (sched)
+        kern_dyn<<<grid, kWarps * 32, smem, stream>>>(a.tmap, (float *)a.samples, a.ld, (V *)a.coef, a.modes, n_groups, a.n_rows, a.T, a.n_bands, a.use_tma,
+                                                      a.dbg, 0x8000000080000000ull, slice_tiles, sched);
+    else
+        kern<<<grid, kWarps * 32, smem, stream>>>(a.tmap, (float *)a.samples, a.ld, (V *)a.coef, a.modes, n_groups, a.n_rows, a.T, a.n_bands, a.use_tma,
+                                                  a.dbg, 0x8000000080000000ull, 0u, nullptr);
     return cudaGetLastError();
 }
 

@@ -28,7 +28,7 @@ struct EqLaunch {
     uint32_t T;
     uint32_t n_bands;
     uint32_t use_tma;
-    uint32_t dbg;          // diagnostics only (env DSPI_DBG): 1 = skip arithmetic, 2 = skip HBM traffic, 4 = force column path, 8 = static schedule
+    uint32_t dbg;          // diagnostics only (env DSPI_DBG): 1 = skip arithmetic, 2 = skip HBM traffic, 4 = force column path, 8 = dynamic time-slice schedule
     uint32_t *sched;       // K1 dynamic scheduler words: [0] item counter, [1 + g] slices completed by group g (or nullptr)
     int n_sms;             // SM count of the device
 };
