@@ -27,6 +27,7 @@
 #include <new>
 #include <vector>
 
+#include "eq_kernels.cuh"
 #include "eq_core.cuh"
 #include "chain_pdm.cuh"
 

@@ -1,8 +1,20 @@
 // dspi_common.cuh — sm_100a device helpers: mbarrier, TMA (cp.async.bulk.tensor), proxies.
 #pragma once
+#ifdef __CUDACC_RTC__
+// runtime compilation (eq_jit.cu): no host headers; the tensor map is an opaque 128-byte parameter
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+typedef unsigned long long size_t_rtc;
+struct alignas(64) CUtensorMap { unsigned long long opaque[16]; };
+#else
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace dspi {
 

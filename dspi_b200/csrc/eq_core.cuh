@@ -4,7 +4,7 @@
 // holds all bands of one channel (or channel pair) in registers and runs a register tile of
 // kSub samples through them.  Reference: dsp_process_channel_block(), dsp_pipeline.c:281-365.
 #pragma once
-#include "eq_kernels.cuh"
+#include "eq_modes.cuh"
 
 namespace dspi {
 namespace core {
@@ -374,6 +374,35 @@ struct EqBank {
             }
         }
         static_assert(NB % 2 == 0, "results must land back in x");
+    }
+
+    // ---- compile-time signature: every band's topology is a template constant ------------------
+    // (runtime-compiled kernels for engines whose channels all share one topology vector: the whole
+    // cascade becomes one straight-line block like the all-biquad case, for any mix of SVF / TDF2)
+    template <unsigned long long W, int B, bool IN_X>
+    __device__ __forceinline__ void sig_from(V (&x)[kSub], V (&y)[kSub], const V nz)
+    {
+        if constexpr (B < NB) {
+            constexpr uint32_t m = (uint32_t)((W >> (4 * B)) & 15ull);
+            V(&in)[kSub] = IN_X ? x : y;
+            V(&out)[kSub] = IN_X ? y : x;
+            if constexpr (m == kModeBypass) {
+                sig_from<W, B + 1, IN_X>(x, y, nz);
+            } else {
+                if constexpr (m == kModeTdf2) tdf2_tile<FUSED>(in, out, c[B], st[B][0], st[B][1], nz);
+                else svf_tile<FUSED, (int)m>(in, out, c[B], st[B][0], st[B][1], nz);
+                sig_from<W, B + 1, !IN_X>(x, y, nz);
+            }
+        } else if constexpr (!IN_X) {
+#pragma unroll
+            for (int i = 0; i < kSub; i++) x[i] = y[i];
+        }
+    }
+    template <unsigned long long W>
+    __device__ __forceinline__ void run_sig(V (&x)[kSub], const V nz)
+    {
+        V y[kSub];
+        sig_from<W, 0, true>(x, y, nz);
     }
 
     // one band over n samples (n % 4 == 0) stored as a lane-private column: sample i at col[i * 32]

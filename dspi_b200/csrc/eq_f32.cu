@@ -22,228 +22,23 @@
 // firmware's FZ mode (main.c:593-600).  Negations are kept out of the inner loops (packed
 // ops have no free negate): a1/a2 are stored negated, `a - b` is fma(b, -1, a) (exact), and
 // the SVF state alternates sign every sample (see svf_tile() in eq_core.cuh).
-#include "eq_core.cuh"
+#include "eq_kernels.cuh"
+#include "eq_f32_kernel.cuh"
 
 namespace dspi {
 namespace {
 
 using namespace core;
-
-constexpr int kTileT = 32;          // samples per shared-memory tile row: 128 B == swizzle span
-constexpr int kStages = 3;
+using k1::kStages;
+using k1::kTileT;
 
 template <typename V, bool FUSED, int NB, bool DYN>
 __global__ void __launch_bounds__(256 * 2 / Lanes<V>::CPL, 1)
 eq_f32_kernel(const __grid_constant__ CUtensorMap tmap, float *__restrict__ samples, uint32_t ld, V *__restrict__ coef,
-              const uint64_t *__restrict__ modes, uint32_t n_groups, uint32_t n_rows, uint32_t T, uint32_t nb_active, uint32_t use_tma, uint32_t dbg, unsigned long long nz_bits, uint32_t slice_tiles, uint32_t *__restrict__ sched)
+              const uint64_t *__restrict__ modes, uint32_t n_groups, uint32_t n_rows, uint32_t T, uint32_t nb_active, uint32_t use_tma, uint32_t dbg,
+              unsigned long long nz_bits, uint32_t slice_tiles, uint32_t *__restrict__ sched)
 {
-    constexpr int CPL = Lanes<V>::CPL;
-    constexpr int kRows = 32 * CPL;
-    constexpr int kWarps = 16 / CPL;
-    constexpr uint32_t kStageBytes = kRows * kTileT * 4;
-
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bars[kWarps][kStages];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    uint8_t *my_smem = smem_raw + (size_t)warp * kStages * kStageBytes;
-    uint64_t *full = bars[warp];
-    if (lane == 0) {
-        if (use_tma) prefetch_tmap(&tmap);
-        for (int s = 0; s < kStages; s++) mbar_init(&full[s], 1);
-        fence_mbar_init();
-    }
-    __syncwarp();
-
-    const V nz = v_bits<V>(nz_bits);                            // (-0.0, -0.0): see mulx()
-    const uint32_t ntiles = (T + kTileT - 1) / kTileT;
-    const bool mem_on = !(dbg & 2u);                            // diagnostics: DSPI_DBG=2 runs the arithmetic without HBM traffic
-    const uint32_t sw = (lane & 7) << 4;                        // 128B-swizzle XOR for this lane's rows
-
-    // ---- work distribution -------------------------------------------------------------------
-    // A work item is (group g, time slice k): `slice_tiles` consecutive tiles of the 32*CPL channels
-    // of group g.  Static mode (sched == nullptr): one item per warp = the whole launch of group
-    // blockIdx.x * kWarps + warp.  Dynamic mode: a persistent grid pulls items from an atomic counter
-    // in slice-major order; the filter state of a group travels from slice to slice through the
-    // coefficient store, ordered by a per-group completion counter (release/acquire).  65536
-    // channels are 1024 groups for 592 warp schedulers: no static split can load them evenly, the
-    // time slices can.
-    const uint32_t n_slices = DYN ? (ntiles + slice_tiles - 1) / slice_tiles : 1;
-    const uint32_t n_items = DYN ? n_groups * n_slices : 0;
-    uint32_t tcount = 0;                                        // tiles this warp has pushed through its ring (stage / parity bookkeeping)
-    for (;;) {
-        uint32_t g, tile_begin, tile_end, slice = 0;
-        if constexpr (DYN) {
-            uint32_t item = 0;
-            if (lane == 0) item = atomicAdd(&sched[0], 1u);
-            item = __shfl_sync(0xffffffffu, item, 0);
-            if (item >= n_items) break;
-            slice = item / n_groups;
-            g = item - slice * n_groups;
-            tile_begin = slice * slice_tiles;
-            tile_end = min(ntiles, tile_begin + slice_tiles);
-            if (slice > 0) {                                    // wait until the previous slice of this group has published its state
-                if (lane == 0) {
-                    const volatile uint32_t *flag = sched + 1 + g;
-                    while (*flag < slice) __nanosleep(100);
-                    __threadfence();
-                }
-                __syncwarp();
-            }
-        } else {
-            g = blockIdx.x * kWarps + warp;
-            if (g >= n_groups) break;                           // warps are fully independent
-            tile_begin = 0;
-            tile_end = ntiles;
-        }
-        const int c0 = g * kRows;                               // first channel (row) of this group
-
-        auto issue_load = [&](uint32_t tile, uint32_t seq) {    // lane 0 only; seq = position in this warp's ring sequence
-            const uint32_t s = seq % kStages;
-            mbar_arrive_expect_tx(&full[s], kStageBytes);
-            tma_load_2d(my_smem + s * kStageBytes, &tmap, &full[s], tile * kTileT, c0);
-        };
-        if (use_tma && mem_on && lane == 0) {
-            if constexpr (DYN) tma_store_wait_read<0>();        // ring buffers of the previous item are drained
-            for (uint32_t j = 0; j + 1 < kStages && tile_begin + j < tile_end; j++) issue_load(tile_begin + j, tcount + j);
-        }
-
-        // ---- coefficients, state and topology of every band -> registers ----------------------
-        EqBank<V, FUSED, NB> bank;
-        V *my_coef = coef + (size_t)g * kMaxBands * 8 * 32 + lane;
-        {
-            const uint64_t *mp[CPL];
-#pragma unroll
-            for (int h = 0; h < CPL; h++) mp[h] = modes + (size_t)g * kRows + h * 32 + lane;
-            bank.load(my_coef, mp, nb_active, DYN);
-        }
-
-        // ---- stream the tiles of this item --------------------------------------------------------
-        for (uint32_t tile = tile_begin; tile < tile_end; tile++, tcount++) {
-            const uint32_t s = tcount % kStages;
-            uint8_t *buf = my_smem + s * kStageBytes;
-            if (use_tma) {
-                if (mem_on) mbar_wait(&full[s], (tcount / kStages) & 1);
-            } else {                                                // plain-load fallback (odd strides / unaligned bases)
-                const uint32_t t = tile * kTileT + lane;
-                for (int r = 0; r < kRows; r++) {
-                    const uint32_t ch = c0 + r;
-                    float v = 0.0f;
-                    if (t < T && ch < n_rows) v = samples[(size_t)ch * ld + t];
-                    *reinterpret_cast<float *>(buf + r * 128 + ((((lane >> 2) << 4) ^ ((r & 7) << 4)) | ((lane & 3) << 2))) = v;
-                }
-                __syncwarp();
-            }
-
-            const int tile_valid = min((int)kTileT, (int)(T - tile * kTileT));
-            if (bank.all_tdf2 && tile_valid == kTileT && !(dbg & 4u)) {
-                // ---- all-biquad warps: register tiles of kSub samples, straight-line over the 10 bands ----
-    #pragma unroll 1
-                for (int sub = 0; sub < kTileT / kSub; sub++) {
-                    // two 16-byte chunks per row per sub-tile; chunk index XOR (row & 7)
-                    V x[kSub];
-                    float4 q[CPL][2];
-    #pragma unroll
-                    for (int h = 0; h < CPL; h++) {
-                        const uint8_t *row = buf + (lane + 32 * h) * 128;
-                        q[h][0] = *reinterpret_cast<const float4 *>(row + (((2 * sub) << 4) ^ sw));
-                        q[h][1] = *reinterpret_cast<const float4 *>(row + (((2 * sub + 1) << 4) ^ sw));
-                    }
-    #pragma unroll
-                    for (int i = 0; i < kSub; i++) {
-                        float part[CPL];
-    #pragma unroll
-                        for (int h = 0; h < CPL; h++) {
-                            const float4 &qq = q[h][i >> 2];
-                            part[h] = (i & 3) == 0 ? qq.x : (i & 3) == 1 ? qq.y : (i & 3) == 2 ? qq.z : qq.w;
-                        }
-                        v_make(x[i], part);
-                    }
-                    if (!(dbg & 1u)) bank.run(x, kSub, nz);            // DSPI_DBG=1: data path only
-    #pragma unroll
-                    for (int h = 0; h < CPL; h++) {
-                        uint8_t *row = buf + (lane + 32 * h) * 128;
-                        *reinterpret_cast<float4 *>(row + (((2 * sub) << 4) ^ sw)) =
-                            make_float4(Lanes<V>::get(x[0], h), Lanes<V>::get(x[1], h), Lanes<V>::get(x[2], h), Lanes<V>::get(x[3], h));
-                        *reinterpret_cast<float4 *>(row + (((2 * sub + 1) << 4) ^ sw)) =
-                            make_float4(Lanes<V>::get(x[4], h), Lanes<V>::get(x[5], h), Lanes<V>::get(x[6], h), Lanes<V>::get(x[7], h));
-                    }
-                }
-            } else {
-                // ---- any other topology: band-outer over the tile, re-laid out in place as lane-private
-                //      columns of CPL-vectors (sample n of this lane at col[n * 32]) ----
-                float4 q[CPL][8];
-    #pragma unroll
-                for (int h = 0; h < CPL; h++) {
-                    const uint8_t *row = buf + (lane + 32 * h) * 128;
-    #pragma unroll
-                    for (int k = 0; k < 8; k++) q[h][k] = *reinterpret_cast<const float4 *>(row + ((k << 4) ^ sw));
-                }
-                __syncwarp();                                       // every row is in registers before columns overwrite them
-                V *col = reinterpret_cast<V *>(buf) + lane;
-    #pragma unroll
-                for (int n = 0; n < kTileT; n++) {
-                    float part[CPL];
-    #pragma unroll
-                    for (int h = 0; h < CPL; h++) {
-                        const float4 &qq = q[h][n >> 2];
-                        part[h] = (n & 3) == 0 ? qq.x : (n & 3) == 1 ? qq.y : (n & 3) == 2 ? qq.z : qq.w;
-                    }
-                    V v;
-                    v_make(v, part);
-                    col[n * 32] = v;
-                }
-                if (!(dbg & 1u)) bank.run_columns(col, tile_valid, nz);
-                float back[CPL][kTileT];
-    #pragma unroll
-                for (int n = 0; n < kTileT; n++) {
-                    const V v = col[n * 32];
-    #pragma unroll
-                    for (int h = 0; h < CPL; h++) back[h][n] = Lanes<V>::get(v, h);
-                }
-                __syncwarp();
-    #pragma unroll
-                for (int h = 0; h < CPL; h++) {
-                    uint8_t *row = buf + (lane + 32 * h) * 128;
-    #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        *reinterpret_cast<float4 *>(row + ((k << 4) ^ sw)) = make_float4(back[h][4 * k], back[h][4 * k + 1], back[h][4 * k + 2], back[h][4 * k + 3]);
-                }
-            }
-
-            if (use_tma) {
-                fence_proxy_async_smem();                           // my smem writes -> async proxy
-                __syncwarp();
-                if (lane == 0 && mem_on) {
-                    tma_store_2d(&tmap, buf, tile * kTileT, c0);
-                    tma_store_commit();
-                    const uint32_t nxt = tile + kStages - 1;        // refill the buffer stored one iteration ago
-                    if (nxt < tile_end) {
-                        tma_store_wait_read<1>();
-                        issue_load(nxt, tcount + kStages - 1);
-                    }
-                }
-            } else {
-                __syncwarp();
-                const uint32_t t = tile * kTileT + lane;
-                for (int r = 0; r < kRows; r++) {
-                    const uint32_t ch = c0 + r;
-                    const float v = *reinterpret_cast<const float *>(buf + r * 128 + ((((lane >> 2) << 4) ^ ((r & 7) << 4)) | ((lane & 3) << 2)));
-                    if (t < T && ch < n_rows) samples[(size_t)ch * ld + t] = v;
-                }
-                __syncwarp();
-            }
-        }
-
-
-        bank.store(my_coef, DYN);                                // filter state back to the coefficient store
-        if constexpr (!DYN) break;
-        __threadfence();                                        // state visible before the slice counter moves
-        __syncwarp();
-        if (lane == 0) atomicExch(&sched[1 + g], slice + 1);
-    }
-    if (use_tma && lane == 0) tma_store_wait_all<0>();          // smem must outlive the bulk reads
+    k1::eq_f32_body<V, FUSED, NB, DYN, k1::NoSig>(tmap, samples, ld, coef, modes, n_groups, n_rows, T, nb_active, use_tma, dbg, nz_bits, slice_tiles, sched);
 }
 
 template <typename V, bool FUSED, int NB>

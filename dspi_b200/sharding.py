@@ -29,17 +29,18 @@ def scatter_rows(full, total_rows, row_len, dtype, device, root=0):
         mine.copy_(full[lo:hi])
         return mine
     if rank == root:
-        reqs = []
+        ops = []
         for r in range(world):
             rlo, rhi = shard_range(total_rows, r, world)
             if r == root:
                 mine.copy_(full[rlo:rhi])
             else:
-                reqs.append(dist.isend(full[rlo:rhi].contiguous(), dst=r))
-        for q in reqs:
+                ops.append(dist.P2POp(dist.isend, full[rlo:rhi], r))      # contiguous row blocks: no staging copy
+        for q in dist.batch_isend_irecv(ops):                              # one grouped NCCL launch for all peers
             q.wait()
     else:
-        dist.recv(mine, src=root)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, mine, root)]):
+            q.wait()
     return mine
 
 
@@ -50,15 +51,16 @@ def gather_rows(mine, total_rows, root=0):
         return mine
     if rank == root:
         full = torch.empty((total_rows, mine.shape[1]), dtype=mine.dtype, device=mine.device)
-        reqs = []
+        ops = []
         for r in range(world):
             rlo, rhi = shard_range(total_rows, r, world)
             if r == root:
                 full[rlo:rhi].copy_(mine)
             else:
-                reqs.append(dist.irecv(full[rlo:rhi], src=r))
-        for q in reqs:
+                ops.append(dist.P2POp(dist.irecv, full[rlo:rhi], r))
+        for q in dist.batch_isend_irecv(ops):
             q.wait()
         return full
-    dist.send(mine.contiguous(), dst=root)
+    for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine.contiguous(), root)]):
+        q.wait()
     return None
