@@ -21,6 +21,7 @@ SYMBOLS = [
     "dspi_last_error", "dspi_device_count", "dspi_compute_coefficients_f32", "dspi_compute_coefficients_q28",
     "dspi_eq_create", "dspi_eq_destroy", "dspi_eq_upload_biquads", "dspi_eq_download_biquads", "dspi_eq_set_param",
     "dspi_eq_process_device", "dspi_eq_process_host", "dspi_eq_sync", "dspi_eq_stream", "dspi_eq_launch_count",
+    "dspi_eq_kernel_info",
     "dspi_host_alloc", "dspi_host_free",
     "dspi_chain_create", "dspi_chain_destroy", "dspi_chain_set_params", "dspi_chain_upload_biquads", "dspi_chain_download_biquads",
     "dspi_chain_reset_state", "dspi_chain_process_host", "dspi_chain_process_device", "dspi_chain_sync", "dspi_chain_stream",
@@ -74,6 +75,7 @@ def lib():
         h.dspi_eq_stream.restype = vp
         h.dspi_eq_launch_count.argtypes = [vp]
         h.dspi_eq_launch_count.restype = C.c_uint64
+        h.dspi_eq_kernel_info.argtypes = [vp, C.c_char_p, C.c_size_t]
         h.dspi_chain_create.argtypes = [C.POINTER(vp), C.POINTER(_ChainDesc)]
         h.dspi_chain_destroy.argtypes = [vp]
         h.dspi_chain_set_params.argtypes = [vp, u32, u32, vp]
@@ -215,6 +217,12 @@ class EqEngine:
     @property
     def launch_count(self):
         return int(lib().dspi_eq_launch_count(self._h))
+
+    def kernel_info(self):
+        """Which kernel the next process call runs (triggers a pending run-time specialisation)."""
+        buf = C.create_string_buffer(320)
+        _check(lib().dspi_eq_kernel_info(self._h, buf, len(buf)))
+        return buf.value.decode()
 
 
 class ChainEngine:

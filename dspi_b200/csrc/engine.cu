@@ -6,9 +6,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <vector>
 
 #include "eq_kernels.cuh"
+#include "eq_jit.h"
 
 namespace {
 
@@ -79,6 +82,10 @@ struct dspi_eq {
     CUtensorMap tmap;
     void *tm_ptr;
     uint32_t tm_T, tm_ld, tm_rows;
+    // kernel choice (float engines): re-derived after every coefficient upload
+    bool sig_dirty;
+    void *jit;               // run-time specialised K1 (eq_jit.cu) or nullptr = ahead-of-time kernels
+    char kinfo[320];
 };
 
 extern "C" {
@@ -125,6 +132,7 @@ int dspi_eq_create(dspi_eq **out, const dspi_eq_desc *desc)
     if (!e) return fail(DSPI_ENOMEM, "host allocation failed");
     memset(e, 0, sizeof(*e));
     e->desc = *desc;
+    e->sig_dirty = true;
     const bool q28 = desc->arith == DSPI_ARITH_Q28;
     e->cpl = 2;
     if (const char *v = getenv("DSPI_F32_CPL")) e->cpl = atoi(v) == 1 ? 1 : 2;   // 1 = scalar FFMA variant, for A/B measurement
@@ -211,6 +219,7 @@ int dspi_eq_upload_biquads(dspi_eq *e, uint32_t ch0, uint32_t n, const void *biq
     else
         CU_OK(dspi::launch_pack_f32((const dspi_biquad_f32 *)e->d_aos, ch0, n, (float *)e->d_coef, e->d_modes, e->cpl, e->stream));
     e->launches++;
+    e->sig_dirty = true;
     CU_OK(cudaStreamSynchronize(e->stream));     // the caller may reuse `biquads` immediately
     return DSPI_OK;
 }
@@ -261,6 +270,59 @@ static int make_tmap(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint3
     return DSPI_OK;
 }
 
+// Pick the K1 variant for the engine's current coefficient set: sample the per-channel topology words
+// the pack kernel wrote, and if one vector dominates (and it is not the all-biquad vector the
+// ahead-of-time kernel already runs straight-line) compile K1 for it.  Only speed depends on this.
+static int refresh_kernel_choice(dspi_eq *e)
+{
+    e->sig_dirty = false;
+    e->jit = nullptr;
+    if (e->desc.arith == DSPI_ARITH_Q28) { snprintf(e->kinfo, sizeof(e->kinfo), "aot q28 cascade (K2)"); return DSPI_OK; }
+    if (e->cpl != 2) { snprintf(e->kinfo, sizeof(e->kinfo), "aot scalar generic (DSPI_F32_CPL=1)"); return DSPI_OK; }
+    const uint32_t C = e->desc.n_channels, nb = e->desc.n_bands;
+    const int nbt = nb <= 10 ? 10 : 12;
+    const uint32_t step = C > 2048 ? C / 2048 : 1;
+    const uint32_t cnt = (C + step - 1) / step;
+    std::vector<uint64_t> w(cnt);
+    CU_OK(cudaMemcpy2DAsync(w.data(), 8, e->d_modes, (size_t)step * 8, 8, cnt, cudaMemcpyDeviceToHost, e->stream));
+    CU_OK(cudaStreamSynchronize(e->stream));
+    const uint64_t mask = (1ull << (4 * nb)) - 1;                // nb <= 12
+    for (auto &x : w) x &= mask;
+    std::vector<uint64_t> sorted(w);
+    std::sort(sorted.begin(), sorted.end());
+    uint64_t best = 0;
+    uint32_t best_n = 0;
+    for (uint32_t i = 0; i < cnt;) {
+        uint32_t j = i;
+        while (j < cnt && sorted[j] == sorted[i]) j++;
+        if (j - i > best_n) { best_n = j - i; best = sorted[i]; }
+        i = j;
+    }
+    uint64_t tdf2 = 0;
+    for (int b = 0; b < nbt; b++) tdf2 |= (uint64_t)dspi::kModeTdf2 << (4 * b);
+    const unsigned pct = (unsigned)(100ull * best_n / cnt);
+    if (best == tdf2 && (int)nb == nbt) {
+        snprintf(e->kinfo, sizeof(e->kinfo), "aot straight-line biquad (%u%% of sampled channels are all-TDF2)", pct);
+        return DSPI_OK;
+    }
+    bool force = false;
+    const bool on = dspi::jit::enabled_by_env(&force);
+    const char *why = nullptr;
+    if (!on) why = "DSPI_JIT=0";
+    else if (best == 0) why = "all bands bypassed";
+    else if (2 * best_n < cnt) why = "no dominant topology vector";
+    else if (!force && C < 1024) why = "engine below 1024 channels (DSPI_JIT=force overrides)";
+    if (why) {
+        snprintf(e->kinfo, sizeof(e->kinfo), "aot generic column path (%s)", why);
+        return DSPI_OK;
+    }
+    char msg[256] = "";
+    e->jit = dspi::jit::acquire(best, e->desc.arith == DSPI_ARITH_F32_FUSED, nbt, e->desc.device, msg, sizeof(msg));
+    if (e->jit) snprintf(e->kinfo, sizeof(e->kinfo), "jit sig=0x%llx nb=%d (%u%% of sampled channels)", (unsigned long long)best, nbt, pct);
+    else snprintf(e->kinfo, sizeof(e->kinfo), "aot generic column path (jit unavailable: %.200s)", msg);
+    return DSPI_OK;
+}
+
 // launch over groups [g0, g0 + ng) of the engine on `stream`; d_samples points at the first row of
 // group g0 and holds `n_rows` valid rows
 static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint32_t g0, uint32_t ng, uint32_t n_rows, cudaStream_t stream)
@@ -291,10 +353,30 @@ static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint3
     a.use_tma = tma_ok ? 1u : 0u;
     if (const char *v = getenv("DSPI_DBG")) a.dbg = (uint32_t)atoi(v);
     cudaError_t err;
+    if (e->sig_dirty) {
+        int rc = refresh_kernel_choice(e);
+        if (rc) return rc;
+    }
     if (q28) err = dspi::launch_eq_q28(a, stream);
-    else err = dspi::launch_eq_f32(a, e->desc.arith == DSPI_ARITH_F32_FUSED, e->cpl, stream);
+    else if (e->jit && !(a.dbg & 12u)) {
+        char msg[200] = "";
+        err = dspi::jit::launch(e->jit, a, stream, msg, sizeof(msg));
+        if (err != cudaSuccess) return fail(DSPI_ECUDA, "%s", msg);
+    } else err = dspi::launch_eq_f32(a, e->desc.arith == DSPI_ARITH_F32_FUSED, e->cpl, stream);
     if (err != cudaSuccess) return fail(DSPI_ECUDA, "EQ kernel launch: %s", cudaGetErrorString(err));
     e->launches++;
+    return DSPI_OK;
+}
+
+int dspi_eq_kernel_info(dspi_eq *e, char *buf, size_t cap)
+{
+    if (!e || !buf || cap == 0) return fail(DSPI_EINVAL, "null argument");
+    CU_OK(cudaSetDevice(e->desc.device));
+    if (e->sig_dirty) {
+        int rc = refresh_kernel_choice(e);
+        if (rc) return rc;
+    }
+    snprintf(buf, cap, "%s", e->kinfo);
     return DSPI_OK;
 }
 

@@ -398,6 +398,15 @@ struct EqBank {
             for (int i = 0; i < kSub; i++) x[i] = y[i];
         }
     }
+    // does every channel of this warp carry exactly the topology vector W (bands >= nb masked off)?
+    template <unsigned long long W>
+    __device__ __forceinline__ bool sig_match() const
+    {
+        bool mine = true;
+#pragma unroll
+        for (int h = 0; h < CPL; h++) mine = mine && mode_h[h] == W;
+        return __all_sync(0xffffffffu, mine);
+    }
     template <unsigned long long W>
     __device__ __forceinline__ void run_sig(V (&x)[kSub], const V nz)
     {

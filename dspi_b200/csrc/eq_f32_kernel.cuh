@@ -101,6 +101,10 @@ __device__ __forceinline__ void eq_f32_body(const CUtensorMap &tmap, float *__re
             for (int h = 0; h < CPL; h++) mp[h] = modes + (size_t)g * kRows + h * 32 + lane;
             bank.load(my_coef, mp, nb_active, DYN);
         }
+        // register-tile (straight-line) path: all-biquad warps in the ahead-of-time kernels; warps whose
+        // channels all carry the compiled-in topology vector in a runtime-specialised kernel
+        bool straight = bank.all_tdf2;
+        if constexpr (SIG::enabled) straight = bank.template sig_match<SIG::word>();
 
         // ---- stream the tiles of this item --------------------------------------------------------
         for (uint32_t tile = tile_begin; tile < tile_end; tile++, tcount++) {
@@ -120,7 +124,7 @@ __device__ __forceinline__ void eq_f32_body(const CUtensorMap &tmap, float *__re
             }
 
             const int tile_valid = min((int)kTileT, (int)(T - tile * kTileT));
-            if ((SIG::enabled || bank.all_tdf2) && tile_valid == kTileT && !(dbg & 4u)) {
+            if (straight && tile_valid == kTileT && !(dbg & 4u)) {
                 // ---- all-biquad warps: register tiles of kSub samples, straight-line over the 10 bands ----
     #pragma unroll 1
                 for (int sub = 0; sub < kTileT / kSub; sub++) {

@@ -144,6 +144,11 @@ int dspi_eq_sync(dspi_eq *e);
 void *dspi_eq_stream(dspi_eq *e);
 /* number of kernel launches issued by this engine so far */
 uint64_t dspi_eq_launch_count(dspi_eq *e);
+/* Which K1/K2 kernel the next dspi_eq_process_* call will run, as text ("jit sig=0x...", "aot
+ * straight-line biquad", "aot generic ...").  Float engines whose channels share one band-topology
+ * vector get a kernel compiled for that vector at run time (NVRTC); this call triggers that
+ * compilation if it is pending.  Results never depend on the choice.  No reference counterpart. */
+int dspi_eq_kernel_info(dspi_eq *e, char *buf, size_t cap);
 
 /* ---- full signal chain: many independent DSPi device instances ------------------------------ */
 /* One instance = process_audio_packet() of one RP2350-shape device (usb_audio.c:500-1317, float

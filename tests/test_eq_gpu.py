@@ -182,3 +182,73 @@ def test_full_size_properties(flavour, Cn):
     ysmall, _ = _run_gpu(flavour, bq, x)
     assert np.array_equal(y[::512].view(np.uint32), ysmall.view(np.uint32))
     assert np.array_equal(y[1::512].view(np.uint32), x.view(np.uint32))
+
+
+# ---- run-time specialised K1 (eq_jit.cu): same bits as the generic kernels and the oracle ----------
+def _run_gpu_info(flavour, bq, x, n_bands=10):
+    Cn, T = x.shape
+    eng = api.EqEngine(flavour, Cn, n_bands)
+    try:
+        eng.upload(bq)
+        info = eng.kernel_info()
+        buf = torch.from_numpy(x).cuda()
+        eng.process_device(buf.data_ptr(), T, T)
+        eng.sync()
+        return buf.cpu().numpy(), eng.download(), info
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "f32s"])
+def test_specialised_kernel_matches_oracle(oracle, flavour, monkeypatch):
+    """Variant B (9 SVF + 1 TDF2 at 96 kHz): every channel shares one topology vector -> NVRTC kernel.
+    200 channels (ragged last group) x 100 samples (3 register tiles + a ragged tail tile)."""
+    monkeypatch.setenv("DSPI_JIT", "force")
+    fs, Cn, T = 96000.0, 200, 100
+    bq = _coeffs("B", Cn, fs, False)
+    x = W.inputs_f32(Cn, T)
+    x[3] = 0; x[3, 0] = 1.0
+    y, st, info = _run_gpu_info(flavour, bq, x)
+    assert info.startswith("jit sig=0x"), info
+    want, wst = _oracle(oracle, flavour, bq, x)
+    _assert_float_equal(y, want)
+    assert same_bits(st, wst)
+    monkeypatch.setenv("DSPI_JIT", "0")
+    y2, st2, info2 = _run_gpu_info(flavour, bq, x)
+    assert info2.startswith("aot generic"), info2
+    assert same_bits(y2, y) and same_bits(st2, st)
+
+
+def test_specialised_kernel_with_foreign_channels(oracle, monkeypatch):
+    """A dominant topology vector plus channels that differ from it (other types, bypassed bands, 8 of
+    the 10 bands active): warps that do not match fall back to the generic path inside the same kernel."""
+    monkeypatch.setenv("DSPI_JIT", "force")
+    fs, Cn, T = 96000.0, 320, 256
+    bq = _coeffs("B", Cn, fs, False)
+    other = _coeffs("mixed", Cn, fs, False, seed=11)
+    for c in list(range(64, 128)) + [130, 200, 319]:
+        bq[c] = other[c]
+    x = W.inputs_f32(Cn, T)
+    y, st, info = _run_gpu_info("f32f", bq, x, n_bands=8)
+    assert info.startswith("jit sig=0x"), info
+    want, wst = _oracle(oracle, "f32f", bq, x, n_bands=8)
+    _assert_float_equal(y, want)
+    assert same_bits(st, wst)
+
+
+def test_kernel_choice_reporting(monkeypatch):
+    monkeypatch.delenv("DSPI_JIT", raising=False)
+    fs = 96000.0
+    eng = api.EqEngine("f32f", 64, 10)
+    try:
+        eng.upload(_coeffs("A", 64, fs, False))
+        assert eng.kernel_info().startswith("aot straight-line biquad")
+        eng.upload(_coeffs("B", 64, fs, False))
+        assert "below 1024 channels" in eng.kernel_info()
+    finally:
+        eng.close()
+    eng = api.EqEngine("q28", 64, 10)
+    try:
+        assert eng.kernel_info().startswith("aot q28")
+    finally:
+        eng.close()
