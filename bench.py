@@ -209,32 +209,10 @@ def extra_configs(api, W, L, torch):
                                            "ms_per_step": ms, "instances": N, "frames": F, "realtime_factor": (F / FS) / (ms * 1e-3),
                                            "bytes_per_instance_frame": {"pcm_in": 6, "spdif_out": 32, "pdm_out": 32}}
         # RP2040-shape Q28 chain: 8192 instances x (4 S/PDIF channels + 1 PDM sub)
-        Pq = np.zeros(N, L.CHAIN_PARAMS_Q28)
-        vol_mul, row = api.host_volume(-20 * 256)
-        tq = api.loudness_table_q28(FS, 83.0, 100.0)
-        for i in range(N):
-            p = Pq[i]
-            p["host_vol_mul"], p["preset_mute_gain"], p["master_volume_q15"] = vol_mul, 1.0, 32768
-            p["preamp_q28"] = [1 << 28, 1 << 28]
-            p["loudness_enabled"], p["crossfeed_enabled"], p["leveller_enabled"], p["leveller_lookahead"] = 1, 1, 1, 1
-            if i == 0:
-                lev = api.leveller_coefficients(FS, 50.0, 0, 15.0, -96.0)
-                xfq = api.crossfeed_coefficients_q28(FS, True, True, 0)
-            p["loudness"], p["crossfeed"], p["leveller"] = tq[row], xfq, lev
-            m = p["matrix"]
-            for o in range(L.CHAINQ_OUTPUTS):
-                oc = m["outputs"][o]
-                oc["enabled"], oc["gain_linear"] = 1, 1.0
-                oc["delay_samples"] = (97 * (o + 1) + 13 * (i % 64)) % 1900
-                for side in range(2):
-                    x = m["crosspoints"][side, o]
-                    sub = o == L.CHAINQ_OUTPUTS - 1
-                    x["enabled"] = 1 if (sub or o % 2 == side) else 0
-                    x["gain_linear"] = 0.5 if sub else 1.0
-        bqq = api.compute_coefficients(W.eq_params("B", L.CHAINQ_EQ_CHANNELS, fs=FS, seed=9), q28=True, fs=FS)
+        Pq, bqq_all = W.chain_config3_q28(N, fs=FS)
         engq = api.ChainEngineQ28(N, max_frames=F)
         engq.set_params(Pq)
-        engq.upload_biquads(np.tile(bqq[None], (N, 1, 1)))
+        engq.upload_biquads(bqq_all)
         spq = torch.empty((N, 2, F, 2), dtype=torch.int32, device="cuda")
         torch.cuda.synchronize()
         engq.process_device(pcm.data_ptr(), 24, npk, fpp, spq.data_ptr(), pdm.data_ptr())
@@ -307,6 +285,7 @@ def main():
     bq = api.compute_coefficients(params, q28=q, fs=FS)
     eng = api.EqEngine(args.arith, Cn, device=local_rank)
     eng.upload(bq)
+    kernel_info = eng.kernel_info()       # float engines compile K1 for their topology vector here, outside the timed region
 
     # rotating input buffers, each larger than L2 (126 MB): 65536 x 6144 x 4 B = 1.5 GiB
     nbuf = max(2, min(8, args.steps))
@@ -356,7 +335,8 @@ def main():
     per_gpu_sps = float(Cn) * T * args.steps / (ms * 1e-3)
     achieved = per_gpu_sps * ALG_BYTES_PER_SAMPLE / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "eq_q28_kernel" if q else "eq_f32_kernel",
+                "peak_source": peak_src, "kernel": "eq_q28_kernel" if q else ("eq_f32_jit" if kernel_info.startswith("jit") else "eq_f32_kernel"),
+                "kernel_variant": kernel_info,
                 "algorithmic_bytes_per_launch": Cn * T * ALG_BYTES_PER_SAMPLE,
                 "note": "FP32-issue bound, not HBM bound: see DESIGN.md (60 FMA-pipe lane-ops per sample)"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")

@@ -30,6 +30,7 @@
 #include "eq_kernels.cuh"
 #include "eq_core.cuh"
 #include "chain_pdm.cuh"
+#include "chain_streams.cuh"
 
 namespace dspi {
 namespace {
@@ -121,13 +122,14 @@ template <bool FUSED, int NB>
 __global__ void __launch_bounds__(128, 1)
 chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F)
 {
-    extern __shared__ float smem[];                       // [warps][kPkt][32]
+    extern __shared__ float smem[];                       // [warps][kPkt][32] packet column + the same again for look-ahead reads
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t side = lane >> 4;
     const uint32_t inst = (blockIdx.x * (blockDim.x >> 5) + warp) * 16 + (lane & 15);
     if ((blockIdx.x * (blockDim.x >> 5) + warp) * 16 >= d.N_pad) return;
     const bool live = inst < d.N;
     float *xs = smem + (size_t)warp * kPkt * 32 + lane;   // xs[t * 32]
+    float *hs = smem + (size_t)(blockDim.x >> 5) * kPkt * 32 + (size_t)warp * kPkt * 32 + lane;   // held look-ahead samples
     const uint32_t Np = d.N_pad;
 
     const uint8_t flags = d.flags[inst];
@@ -172,12 +174,32 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
 
     float peak_in = 0.0f;
     uint16_t clip = 0;
+    const uint32_t f_end = (p0 + n_packets) * fpp;
     for (uint32_t p = p0; p < p0 + n_packets; p++) {
         const uint32_t f0 = p * fpp;
+        // The leveller's look-ahead ring is read one slot per sample, each read just before that slot is
+        // overwritten (leveller.c:231-237), and a packet (<= 192 frames) never laps the 480-slot ring:
+        // all of this packet's reads can be issued now, as asynchronous copies into shared memory that
+        // complete behind passes 1-2, instead of one exposed HBM round trip per sample.
+        if (lev_on && lookahead) {
+            uint32_t idx = la_idx;
+            for (uint32_t i = 0; i < fpp; i++) {
+                cp_async_4(hs + i * 32, la_buf + (size_t)idx * Np);
+                if (++idx >= (uint32_t)kLa) idx = 0;
+            }
+        }
+        cp_async_commit();
         // ---- PASS 1 + loudness + PASS 2 (master EQ), register tiles of 8 ----
         for (uint32_t t0 = 0; t0 < fpp; t0 += kSub) {
             const int nvalid = min((int)kSub, (int)(fpp - t0));
             float x[kSub];
+            if (live) {                                    // next tile's PCM bytes (a private 6 B/frame stream per lane) towards L1
+                const uint32_t fn = f0 + t0 + kSub;
+                if (fn < f_end) {
+                    prefetch_l1(my_pcm + (size_t)fn * bpf);
+                    prefetch_l1(my_pcm + (size_t)(min(fn + (uint32_t)kSub, f_end) - 1) * bpf);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < kSub; i++) {
                 int32_t s = 0;
@@ -253,10 +275,11 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
             float gain, gain_step;
             if (fpp == 1) { gain = new_gain; gain_step = 0.0f; }
             else { gain_step = __fdiv_rn(__fadd_rn(new_gain, -prev_for_ramp), (float)(fpp - 1)); gain = prev_for_ramp; }
+            cp_async_wait_all();                                             // this lane's look-ahead reads have landed
             for (uint32_t i = 0; i < fpp; i++) {                             // :228-259
                 float o = xs[i * 32];
                 if (lev_on && lookahead) {
-                    const float held = la_buf[(size_t)la_idx * Np];
+                    const float held = hs[i * 32];
                     la_buf[(size_t)la_idx * Np] = o;
                     o = held;
                     la_idx++;
@@ -349,6 +372,8 @@ chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint
     const int32_t dly = d.o_dly[o * Np + inst];
     const bool delay_on = (d.flags[inst] & F_ANY_DELAY) && dly > 0;          // usb_audio.c:898-901
     const bool any_delay = d.flags[inst] & F_ANY_DELAY;
+    const bool ring_early = delay_on && dly >= kSub && dly < kMaxDelay;
+    const uint32_t f_end = (p0 + n_packets) * fpp;
     uint32_t widx = d.widx_in[inst];
     float *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;     // one contiguous ring per (output, instance)
 
@@ -360,6 +385,32 @@ chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint
     }
     const bool skip_eq = !enabled || mute;                                   // :878-884
     const int mixcase = !enabled ? 0 : (gl != 0.0f && gr != 0.0f) ? 3 : (gl != 0.0f) ? 1 : (gr != 0.0f) ? 2 : 0;   // :767-778
+
+    // The master L/R rows a tile needs are staged through shared memory by asynchronous copies issued two
+    // tiles ahead (each lane fetches its own instance's samples, so no warp synchronisation is needed):
+    // the load latency (L2 / HBM) overlaps the EQ arithmetic of the tiles in between.
+    constexpr int kLrStages = 3;
+    __shared__ float lr_stage[4][kLrStages][2][kSub][32];
+    float *lr = &lr_stage[warp][0][0][0][lane];
+    const uint32_t tpp = (fpp + kSub - 1) / kSub, n_tiles = n_packets * tpp;
+    auto issue_lr = [&](uint32_t n) {
+        if (n < n_tiles) {
+            const uint32_t pn = p0 + n / tpp, tt = (n % tpp) * kSub;
+            float *dst = lr + (n % kLrStages) * (2 * kSub * 32);
+            const float *src = d.master + ((size_t)pn * fpp + tt) * Np + inst;
+#pragma unroll
+            for (int i = 0; i < kSub; i++) {
+                if (tt + i < fpp) {
+                    if (mixcase & 1) cp_async_4(dst + i * 32, src + (size_t)i * Np);
+                    if (mixcase & 2) cp_async_4(dst + (kSub + i) * 32, src + ((size_t)d.max_frames + i) * Np);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int n = 0; n < kLrStages - 1; n++) issue_lr(n);
+    uint32_t tile_n = 0;
 
     float peak_last = 0.0f;
     uint16_t clip = 0;
@@ -374,12 +425,25 @@ chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint
         for (uint32_t t0 = 0; t0 < fpp; t0 += kSub) {
             const int nvalid = min((int)kSub, (int)(fpp - t0));
             float x[kSub];
+            issue_lr(tile_n + kLrStages - 1);                                // master L/R of the tile two ahead
+            cp_async_wait<kLrStages - 1>();                                  // ... and this tile's have landed
+            const float *cur = lr + (tile_n % kLrStages) * (2 * kSub * 32);
+            tile_n++;
+            // Delay ring (:902-909 is write-then-read per sample).  For kSub <= dly < MAX the slots this
+            // tile reads were written by earlier tiles (and the slots it writes are not read in it), so
+            // the reads are issued NOW and their HBM latency hides behind the matrix + EQ arithmetic.
+            float rd[kSub];
+            if (ring_early) {
+#pragma unroll
+                for (int i = 0; i < kSub; i++)
+                    if (i < nvalid) rd[i] = ring[(w + i - (uint32_t)dly) & (kMaxDelay - 1)];
+            }
 #pragma unroll
             for (int i = 0; i < kSub; i++) {
                 float l = 0.0f, r = 0.0f;
                 if (i < nvalid) {
-                    l = d.master[((size_t)0 * d.max_frames + f0 + t0 + i) * Np + inst];
-                    r = d.master[((size_t)1 * d.max_frames + f0 + t0 + i) * Np + inst];
+                    if (mixcase & 1) l = cur[i * 32];
+                    if (mixcase & 2) r = cur[(kSub + i) * 32];
                 }
                 float v;
                 if (mixcase == 3) v = fm<FUSED>(l, gl, __fmul_rn(r, gr));    // :769
@@ -396,22 +460,14 @@ chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint
                     else if (gain != 1.0f) x[i] = __fmul_rn(x[i], gain);
                 }
             }
-            if (delay_on) {                                                  // :902-909: write, then read, per sample
-                if (dly <= kMaxDelay - kSub) {
-                    // all writes of the tile first, then all (independent) reads: one exposed memory
-                    // latency per tile instead of one per sample.  Safe because a read can only land on a
-                    // slot written LATER in the same tile when dly > MAX_DELAY - kSub.
+            if (ring_early) {
 #pragma unroll
-                    for (int i = 0; i < kSub; i++)
-                        if (i < nvalid) ring[(w + i) & (kMaxDelay - 1)] = x[i];
-#pragma unroll
-                    for (int i = 0; i < kSub; i++)
-                        if (i < nvalid) x[i] = ring[(w + i - (uint32_t)dly) & (kMaxDelay - 1)];
-                } else {
-                    for (int i = 0; i < nvalid; i++) {
-                        ring[(w + i) & (kMaxDelay - 1)] = x[i];
-                        x[i] = ring[(w + i - (uint32_t)dly) & (kMaxDelay - 1)];
-                    }
+                for (int i = 0; i < kSub; i++)
+                    if (i < nvalid) { ring[(w + i) & (kMaxDelay - 1)] = x[i]; x[i] = rd[i]; }
+            } else if (delay_on) {                                           // dly < kSub, or dly == MAX (aliases to 0, SURVEY a-10)
+                for (int i = 0; i < nvalid; i++) {
+                    ring[(w + i) & (kMaxDelay - 1)] = x[i];
+                    x[i] = ring[(w + i - (uint32_t)dly) & (kMaxDelay - 1)];
                 }
             }
             w = (w + nvalid) & (kMaxDelay - 1);
@@ -448,7 +504,7 @@ chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint
 // ---------------------------------------------------------------------------------------------
 // delta-sigma PDM (chain_pdm.cuh): one instance per lane
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 chain_pdm_kernel(ChainDev d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
     const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -538,8 +594,8 @@ using dspi::fail;
 struct dspi_chain {
     dspi_chain_desc desc;
     ChainDev d;
-    cudaStream_t stream, s_pdm;
-    cudaEvent_t ev_slice[4], ev_pdm;
+    cudaStream_t stream;                  // the engine stream callers see; stages run on st.* between ev_begin and ev_done
+    dspi::ChainStreams st;
     dspi_biquad_f32 *d_aos;          // [N_pad][11][12] instance-major mirror of filters[][]
     std::vector<void *> allocs;
     uint64_t launches;
@@ -591,31 +647,34 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
 {
     const uint32_t F = n_packets * fpp;
     auto front = dspi::chain_front_kernel<FUSED, 10>;
-    const size_t smem = (size_t)4 * dspi::kPkt * 32 * 4;
+    const size_t smem = (size_t)2 * 4 * dspi::kPkt * 32 * 4;      // packet column + look-ahead column per warp
     static bool configured = false;
     if (!configured) { CU_OK(cudaFuncSetAttribute(front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
-    // The modulator is one serial chain per instance (256 decisions per frame) and fills only a fraction
-    // of the machine, so the call is cut into packet slices: the PDM kernel of slice k runs on a second
-    // stream while front + outputs of slice k+1 run on the engine stream.  All state lives in HBM
-    // between slices, so the slicing changes no bit.
-    const uint32_t n_slices = n_packets < 4 ? n_packets : 4;
+    // Stage pipeline over packet slices on three streams (chain_streams.cuh).
+    dspi::ChainStreams &st = c->st;
+    const uint32_t n_slices = n_packets < (uint32_t)dspi::ChainStreams::kMaxSlices ? n_packets : (uint32_t)dspi::ChainStreams::kMaxSlices;
+    CU_OK(cudaEventRecord(st.ev_begin, c->stream));
+    CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t p0 = (uint32_t)((uint64_t)n_packets * sl / n_slices), p1 = (uint32_t)((uint64_t)n_packets * (sl + 1) / n_slices);
         const ChainDev d = c->d;
         const uint32_t fwarps = d.N_pad / 16, owarps = d.N_pad / 32 * dspi::kOuts;
-        front<<<(fwarps + 3) / 4, 128, smem, c->stream>>>(d, (const uint8_t *)d_pcm, bit_depth, p0, p1 - p0, fpp, F);
+        front<<<(fwarps + 3) / 4, 128, smem, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, p0, p1 - p0, fpp, F);
         CU_OK(cudaGetLastError());
-        dspi::chain_out_kernel<FUSED, 10><<<(owarps + 3) / 4, 128, 0, c->stream>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        CU_OK(cudaEventRecord(st.ev_front[sl], st.s_front));
+        CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
+        dspi::chain_out_kernel<FUSED, 10><<<(owarps + 3) / 4, 128, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
         CU_OK(cudaGetLastError());
         std::swap(c->d.widx_in, c->d.widx_out);
-        CU_OK(cudaEventRecord(c->ev_slice[sl], c->stream));
-        CU_OK(cudaStreamWaitEvent(c->s_pdm, c->ev_slice[sl], 0));
-        dspi::chain_pdm_kernel<<<(d.N + 127) / 128, 128, 0, c->s_pdm>>>(d, p0 * fpp, p1 * fpp, F, d_pdm);
+        CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
+        CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
+        dspi::chain_pdm_kernel<<<(d.N + 63) / 64, 64, 0, st.s_pdm>>>(d, p0 * fpp, p1 * fpp, F, d_pdm);
         CU_OK(cudaGetLastError());
         c->launches += 3;
     }
-    CU_OK(cudaEventRecord(c->ev_pdm, c->s_pdm));
-    CU_OK(cudaStreamWaitEvent(c->stream, c->ev_pdm, 0));         // later work on the engine stream sees the PDM words
+    // the last modulator launch is ordered after every other stage launch of this call
+    CU_OK(cudaEventRecord(st.ev_done, st.s_pdm));
+    CU_OK(cudaStreamWaitEvent(c->stream, st.ev_done, 0));         // later work on the engine stream sees all outputs
     if (d_status) {
         dspi::chain_status_kernel<<<(c->d.N + 127) / 128, 128, 0, c->stream>>>(c->d, d_status);
         CU_OK(cudaGetLastError());
@@ -643,9 +702,7 @@ int dspi_chain_destroy(dspi_chain *c)
     if (!c) return DSPI_OK;
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->s_pdm) { cudaStreamSynchronize(c->s_pdm); cudaStreamDestroy(c->s_pdm); }
-    for (int i = 0; i < 4; i++) if (c->ev_slice[i]) cudaEventDestroy(c->ev_slice[i]);
-    if (c->ev_pdm) cudaEventDestroy(c->ev_pdm);
+    c->st.destroy();
     for (void *p : c->allocs) cudaFree(p);
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_spdif) cudaFree(c->d_spdif);
@@ -672,9 +729,8 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     CU_OK(cudaSetDevice(desc->device));
     dspi_chain *c = new (std::nothrow) dspi_chain();
     if (!c) return fail(DSPI_ENOMEM, "host allocation failed");
-    c->stream = c->s_pdm = nullptr;
-    c->ev_pdm = nullptr;
-    for (int i = 0; i < 4; i++) c->ev_slice[i] = nullptr;
+    c->stream = nullptr;
+    c->st = dspi::ChainStreams();
     c->d_aos = nullptr; c->launches = 0; c->d_pcm = nullptr; c->pcm_bytes = 0; c->d_spdif = nullptr; c->spdif_bytes = 0;
     c->d_pdmout = nullptr; c->pdmout_bytes = 0; c->d_status = nullptr;
     c->desc = *desc;
@@ -686,13 +742,7 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     d.max_frames = desc->max_frames;
     const size_t Np = d.N_pad;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    {
-        int lo = 0, hi = 0;                                  // the modulator stream gets the highest priority: its few CTAs
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);          // are placed first whenever an SM frees a slot
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->s_pdm, cudaStreamNonBlocking, hi);
-    }
-    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev_slice[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pdm, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = c->st.create();
 #define TRY(x) if (e == cudaSuccess) e = (x)
     TRY(dev_alloc(c, &c->d_aos, Np * dspi::kRoles * DSPI_MAX_BANDS));
     TRY(dev_alloc(c, &d.coef, Np * dspi::kRoles * DSPI_MAX_BANDS * 8));

@@ -20,6 +20,7 @@
 
 #include "eq_kernels.cuh"
 #include "chain_pdm.cuh"
+#include "chain_streams.cuh"
 
 namespace dspi {
 namespace {
@@ -394,7 +395,7 @@ chainq_out_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint3
     if (o == 0) d.widx_out[inst] = widx;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 chainq_pdm_kernel(ChainQ d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
     const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -479,8 +480,8 @@ using dspi::fail;
 struct dspi_chainq {
     dspi_chain_desc desc;
     ChainQ d;
-    cudaStream_t stream, s_pdm;
-    cudaEvent_t ev_slice[4], ev_pdm;
+    cudaStream_t stream;                  // the engine stream callers see; stages run on st.* between ev_begin and ev_done
+    dspi::ChainStreams st;
     dspi_biquad_q28 *d_aos;
     std::vector<void *> allocs;
     uint64_t launches;
@@ -534,9 +535,7 @@ int dspi_chainq_destroy(dspi_chainq *c)
     if (!c) return DSPI_OK;
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->s_pdm) { cudaStreamSynchronize(c->s_pdm); cudaStreamDestroy(c->s_pdm); }
-    for (int i = 0; i < 4; i++) if (c->ev_slice[i]) cudaEventDestroy(c->ev_slice[i]);
-    if (c->ev_pdm) cudaEventDestroy(c->ev_pdm);
+    c->st.destroy();
     for (void *p : c->allocs) cudaFree(p);
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_spdif) cudaFree(c->d_spdif);
@@ -563,9 +562,8 @@ int dspi_chainq_create(dspi_chainq **out, const dspi_chain_desc *desc)
     CU_OK(cudaSetDevice(desc->device));
     dspi_chainq *c = new (std::nothrow) dspi_chainq();
     if (!c) return fail(DSPI_ENOMEM, "host allocation failed");
-    c->stream = c->s_pdm = nullptr;
-    c->ev_pdm = nullptr;
-    for (int i = 0; i < 4; i++) c->ev_slice[i] = nullptr;
+    c->stream = nullptr;
+    c->st = dspi::ChainStreams();
     c->d_aos = nullptr; c->launches = 0; c->d_pcm = nullptr; c->pcm_bytes = 0; c->d_spdif = nullptr; c->spdif_bytes = 0;
     c->d_pdmout = nullptr; c->pdmout_bytes = 0; c->d_status = nullptr;
     c->desc = *desc;
@@ -577,13 +575,7 @@ int dspi_chainq_create(dspi_chainq **out, const dspi_chain_desc *desc)
     d.max_frames = desc->max_frames;
     const size_t Np = d.N_pad;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->s_pdm, cudaStreamNonBlocking, hi);
-    }
-    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->ev_slice[i], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_pdm, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = c->st.create();
 #define TRY(x) if (e == cudaSuccess) e = (x)
     TRY(dev_alloc(c, &c->d_aos, Np * dspi::kRoles * DSPI_MAX_BANDS));
     TRY(dev_alloc(c, &d.bq, Np * dspi::kRoles * DSPI_MAX_BANDS * 8));
@@ -757,24 +749,30 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
         CU_OK(cudaFuncSetAttribute(dspi::chainq_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const uint32_t n_slices = n_packets < 4 ? n_packets : 4;            // PDM of slice k overlaps front + outputs of slice k+1
+    // Stage pipeline over packet slices on three streams (chain_streams.cuh).
+    dspi::ChainStreams &st = c->st;
+    const uint32_t n_slices = n_packets < (uint32_t)dspi::ChainStreams::kMaxSlices ? n_packets : (uint32_t)dspi::ChainStreams::kMaxSlices;
+    CU_OK(cudaEventRecord(st.ev_begin, c->stream));
+    CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t p0 = (uint32_t)((uint64_t)n_packets * sl / n_slices), p1 = (uint32_t)((uint64_t)n_packets * (sl + 1) / n_slices);
         const ChainQ d = c->d;
         const uint32_t fwarps = d.N_pad / 16, owarps = d.N_pad / 32 * dspi::kOuts;
-        dspi::chainq_front_kernel<<<(fwarps + 3) / 4, 128, smem, c->stream>>>(d, (const uint8_t *)d_pcm, bit_depth, p0, p1 - p0, fpp, F);
+        dspi::chainq_front_kernel<<<(fwarps + 3) / 4, 128, smem, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, p0, p1 - p0, fpp, F);
         CU_OK(cudaGetLastError());
-        dspi::chainq_out_kernel<<<(owarps + 3) / 4, 128, smem, c->stream>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        CU_OK(cudaEventRecord(st.ev_front[sl], st.s_front));
+        CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
+        dspi::chainq_out_kernel<<<(owarps + 3) / 4, 128, smem, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
         CU_OK(cudaGetLastError());
         std::swap(c->d.widx_in, c->d.widx_out);
-        CU_OK(cudaEventRecord(c->ev_slice[sl], c->stream));
-        CU_OK(cudaStreamWaitEvent(c->s_pdm, c->ev_slice[sl], 0));
-        dspi::chainq_pdm_kernel<<<(d.N + 127) / 128, 128, 0, c->s_pdm>>>(d, p0 * fpp, p1 * fpp, F, d_pdm);
+        CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
+        CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
+        dspi::chainq_pdm_kernel<<<(d.N + 63) / 64, 64, 0, st.s_pdm>>>(d, p0 * fpp, p1 * fpp, F, d_pdm);
         CU_OK(cudaGetLastError());
         c->launches += 3;
     }
-    CU_OK(cudaEventRecord(c->ev_pdm, c->s_pdm));
-    CU_OK(cudaStreamWaitEvent(c->stream, c->ev_pdm, 0));
+    CU_OK(cudaEventRecord(st.ev_done, st.s_pdm));
+    CU_OK(cudaStreamWaitEvent(c->stream, st.ev_done, 0));
     if (d_status) {
         dspi::chainq_status_kernel<<<(c->d.N + 127) / 128, 128, 0, c->stream>>>(c->d, d_status);
         CU_OK(cudaGetLastError());

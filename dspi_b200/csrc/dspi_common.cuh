@@ -95,6 +95,30 @@ __device__ __forceinline__ void tma_store_wait_all()
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// 4-byte asynchronous copy global -> shared (LDGSTS): no register, completion by cp_async_wait_all()
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()                      // at most N of this thread's groups still pending
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+// pull one 128-byte line towards this SM's L1 (no register, no fault semantics needed: callers pass valid addresses)
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

@@ -157,3 +157,34 @@ def chain_config3(N, fs=96000.0, seed=1, distinct=64):
         bq[i] = api.compute_coefficients(eq_params("B", L.CHAIN_EQ_CHANNELS, fs=fs, seed=seed + i), q28=False, fs=fs)
     reps = (N + D - 1) // D
     return np.tile(P, reps)[:N].copy(), np.tile(bq, (reps, 1, 1))[:N].copy()
+
+
+def chain_config3_q28(N, fs=96000.0, seed=9):
+    """Config 3 on the RP2040 shape (Q28 arithmetic, 2 in -> 4 S/PDIF channels + PDM sub): every stage on,
+    delays 0-1900 samples, one EQ recipe set (variant B) shared by all instances.
+    Returns (CHAIN_PARAMS_Q28 [N], BIQUAD_Q28 [N, 7, 12])."""
+    from . import api
+    P = np.zeros(N, L.CHAIN_PARAMS_Q28)
+    vol_mul, row = api.host_volume(-20 * 256)
+    tq = api.loudness_table_q28(fs, 83.0, 100.0)
+    lev = api.leveller_coefficients(fs, 50.0, 0, 15.0, -96.0)
+    xfq = api.crossfeed_coefficients_q28(fs, True, True, 0)
+    for i in range(min(N, 64)):
+        p = P[i]
+        p["host_vol_mul"], p["preset_mute_gain"], p["master_volume_q15"] = vol_mul, 1.0, 32768
+        p["preamp_q28"] = [1 << 28, 1 << 28]
+        p["loudness_enabled"], p["crossfeed_enabled"], p["leveller_enabled"], p["leveller_lookahead"] = 1, 1, 1, 1
+        p["loudness"], p["crossfeed"], p["leveller"] = tq[row], xfq, lev
+        m = p["matrix"]
+        for o in range(L.CHAINQ_OUTPUTS):
+            oc = m["outputs"][o]
+            oc["enabled"], oc["gain_linear"] = 1, 1.0
+            oc["delay_samples"] = (97 * (o + 1) + 13 * i) % 1900
+            for side in range(2):
+                x = m["crosspoints"][side, o]
+                sub = o == L.CHAINQ_OUTPUTS - 1
+                x["enabled"] = 1 if (sub or o % 2 == side) else 0
+                x["gain_linear"] = 0.5 if sub else 1.0
+    P = np.tile(P[:min(N, 64)], (N + 63) // 64)[:N].copy()
+    bq = api.compute_coefficients(eq_params("B", L.CHAINQ_EQ_CHANNELS, fs=fs, seed=seed), q28=True, fs=fs)
+    return P, np.tile(bq[None], (N, 1, 1))

@@ -19,12 +19,18 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--arith", default="f32f")
 a = ap.parse_args()
 N, F, fs = a.instances, a.packets * a.fpp, 96000.0
-P, bq = W.chain_config3(N, fs=fs, seed=1)
-eng = api.ChainEngine(a.arith, N, max_frames=F)
+q28 = a.arith == "q28"
+if q28:
+    P, bq = W.chain_config3_q28(N, fs=fs)
+    eng = api.ChainEngineQ28(N, max_frames=F)
+else:
+    P, bq = W.chain_config3(N, fs=fs, seed=1)
+    eng = api.ChainEngine(a.arith, N, max_frames=F)
+n_out = 5 if q28 else 9
 eng.set_params(P)
 eng.upload_biquads(bq)
 pcm = torch.randint(0, 256, (N, F * 6), dtype=torch.uint8, device="cuda")
-spdif = torch.empty((N, 4, F, 2), dtype=torch.int32, device="cuda")
+spdif = torch.empty((N, 2 if q28 else 4, F, 2), dtype=torch.int32, device="cuda")
 pdm = torch.empty((N, F, 8), dtype=torch.int32, device="cuda")
 torch.cuda.synchronize()
 st = torch.cuda.ExternalStream(eng.stream)
@@ -38,4 +44,4 @@ e1.record(st)
 eng.sync()
 ms = e0.elapsed_time(e1) / a.reps
 print(json.dumps({"instances": N, "frames": F, "ms_per_step": ms, "instance_frames_per_s": N * F / (ms * 1e-3),
-                  "output_channel_samples_per_s": N * 9 * F / (ms * 1e-3), "realtime_factor": (F / fs) / (ms * 1e-3)}))
+                  "arith": a.arith, "output_channel_samples_per_s": N * n_out * F / (ms * 1e-3), "realtime_factor": (F / fs) / (ms * 1e-3)}))

@@ -3,7 +3,7 @@ rep=sys.argv[1]
 raw=subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
 rows=list(csv.reader(raw.splitlines()))
 hdr,units,vals=rows[0],rows[1],rows[2]
-want=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','smsp__inst_executed.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fma.avg.pct','sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active','sm__pipe_fmaheavy','sm__pipe_fmalite','sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','sm__warps_active.avg.pct_of_peak_sustained_active','sm__cycles_elapsed.avg','launch__grid_size','smsp__average_warp_latency_per_inst_issued','lts__t_bytes.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','smsp__inst_executed_pipe','sm__inst_executed_pipe']
+want=['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','smsp__inst_executed.sum','smsp__issue_active.avg.pct_of_peak_sustained_active','sm__inst_executed_pipe_fma.avg.pct','sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active','sm__pipe_fmaheavy','sm__pipe_fmalite','sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread','sm__warps_active.avg.pct_of_peak_sustained_active','sm__cycles_elapsed.avg','launch__grid_size','smsp__average_warp_latency_per_inst_issued','lts__t_bytes.sum','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','sm__inst_executed_pipe_alu.avg.pct','sm__inst_executed_pipe_fma.avg.pct','sm__inst_executed_pipe_lsu.avg.pct','sm__inst_executed_pipe_fmaheavy.avg.pct','sm__inst_executed_pipe_fmalite.avg.pct','smsp__warps_eligible.avg.per_cycle_active','smsp__issue_active.avg.per_cycle_active','sm__throughput.avg.pct']
 for h,u,v in zip(hdr,units,vals):
     if any(h.startswith(w) for w in want) and 'pct_of_peak_sustained_elapsed' not in h.replace('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','') and '.per_second' not in h:
         print(f"{h} [{u}] = {v}")

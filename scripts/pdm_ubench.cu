@@ -1,0 +1,140 @@
+// pdm_ubench.cu — cycles per delta-sigma decision for several formulations of the inner loop of
+// pdm_generator.c:372-378 (one warp per SM sub-partition, like chain_pdm_kernel at 8192 instances).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/pdm_ubench scripts/pdm_ubench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+template <int V>
+__device__ __forceinline__ uint32_t chunk(int32_t &err1, int32_t &err2, int32_t target, int32_t dither)
+{
+    uint32_t word = 0;
+    if constexpr (V == 0) {                 // reference shape
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const int bit = (err2 + dither) >= 0;
+            const int32_t fb = bit ? 65535 : 0;
+            if (bit) word |= 1u << (31 - k);
+            err1 += target - fb;
+            err2 += err1 - fb;
+        }
+    } else if constexpr (V == 1) {          // mask form (round-1 kernel)
+        int32_t s = err2 + dither;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const int32_t m = s >> 31;
+            const int32_t nfb = ~m & -65535;
+            word = __funnelshift_l((uint32_t)~m, word, 1);
+            err1 += target + nfb;
+            s += err1 + nfb;
+        }
+        err2 = s - dither;
+    } else if constexpr (V == 2) {          // two running sums, predicated corrections
+        int32_t s = err2 + dither, g = err1 + target;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const bool bit = s >= 0;
+            int32_t t = s + g;
+            g += target;
+            if (bit) { t -= 131070; g -= 65535; word |= 1u << (31 - k); }
+            s = t;
+        }
+        err2 = s - dither; err1 = g - target;
+    } else if constexpr (V == 3) {          // two running sums, sign mask times constant on the FMA pipe
+        int32_t s = err2 + dither, g = err1 + target;
+        const int32_t tg = target - 65535;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const int32_t m = s >> 31;                    // 0 when the bit is 1, -1 when it is 0
+            const int32_t t2 = s + g - 131070;
+            const int32_t g2 = g + tg;
+            s = m * -131070 + t2;
+            g = m * -65535 + g2;
+            acc = acc * 2u + (uint32_t)m;
+        }
+        word = acc - 1u;                                   // sum (bit-1) 2^(31-k) = W - (2^32-1)
+        err2 = s - dither; err1 = g - target;
+    } else if constexpr (V == 4) {          // select between the two candidate sums
+        int32_t s = err2 + dither, g = err1 + target;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const int32_t c0 = s + g, c1 = s + g - 131070;
+            const int32_t g0 = g + target, g1 = g + target - 65535;
+            const bool bit = s >= 0;
+            s = bit ? c1 : c0;
+            g = bit ? g1 : g0;
+            word = word * 2u + (bit ? 1u : 0u);
+        }
+        err2 = s - dither; err1 = g - target;
+    } else if constexpr (V == 5) {          // like 3 but the word is assembled from sign masks with one LOP3 per 2 bits
+        int32_t s = err2 + dither, g = err1 + target;
+        const int32_t tg = target - 65535;
+        uint32_t inv = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const int32_t m = s >> 31;
+            const int32_t t2 = s + g - 131070;
+            const int32_t g2 = g + tg;
+            s = m * -131070 + t2;
+            g = m * -65535 + g2;
+            inv |= (uint32_t)m & (1u << (31 - k));
+        }
+        word = ~inv;
+        err2 = s - dither; err1 = g - target;
+    }
+    return word;
+}
+
+template <int V>
+__global__ void k(int32_t *st, uint32_t *out, long long *cyc, int iters)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t err1 = st[tid * 2], err2 = st[tid * 2 + 1];
+    const int32_t target = 32768 + (tid * 37 % 20000) - 10000;
+    uint32_t h = 0;
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        const int32_t dither = (int32_t)((h >> 7) & 255) - 128;
+        h = h * 1664525u + chunk<V>(err1, err2, target, dither);
+        if ((it & 7) == 7) { err1 -= err1 >> 16; err2 -= err2 >> 16; }
+    }
+    const long long t1 = clock64();
+    out[tid] = h ^ (uint32_t)err1 ^ (uint32_t)err2;
+    if (threadIdx.x % 32 == 0) cyc[tid / 32] = t1 - t0;
+}
+
+template <int V>
+void run(const char *name, int32_t *st, uint32_t *out, long long *cyc, int warps_per_sm)
+{
+    const int iters = 4096, nsm = 148;
+    k<V><<<nsm, 32 * warps_per_sm>>>(st, out, cyc, iters);
+    cudaDeviceSynchronize();
+    k<V><<<nsm, 32 * warps_per_sm>>>(st, out, cyc, iters);
+    cudaDeviceSynchronize();
+    static uint32_t h_out[148 * 512];
+    static long long h_cyc[148 * 16];
+    cudaMemcpy(h_out, out, sizeof(uint32_t) * nsm * 32 * warps_per_sm, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h_cyc, cyc, sizeof(long long) * nsm * warps_per_sm, cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < nsm * warps_per_sm; i++) mx = h_cyc[i] > mx ? h_cyc[i] : mx;
+    uint32_t x = 0;
+    for (int i = 0; i < nsm * 32 * warps_per_sm; i++) x = x * 31 + h_out[i];
+    printf("%-28s warps/SM %2d  cycles/bit %.2f  checksum %08x  (%s)\n", name, warps_per_sm, (double)mx / (iters * 32.0), x, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main()
+{
+    int32_t *st; uint32_t *out; long long *cyc;
+    cudaMalloc(&st, 148 * 512 * 8); cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 148 * 16 * 8);
+    cudaMemset(st, 0, 148 * 512 * 8);
+    for (int w : {4, 8, 16}) {
+        run<0>("reference shape", st, out, cyc, w);
+        run<1>("mask form (old)", st, out, cyc, w);
+        run<2>("predicated two-sum", st, out, cyc, w);
+        run<3>("imad two-sum", st, out, cyc, w);
+        run<4>("select two-sum", st, out, cyc, w);
+        run<5>("imad two-sum, lop3 word", st, out, cyc, w);
+    }
+    return 0;
+}
