@@ -1,5 +1,5 @@
-// chain_f32.cu — K3..K9: the whole per-packet float signal chain of one DSPi device, for thousands
-// of independent device instances, sm_100a.
+// chain_f32.cu — the whole per-packet float signal chain of one DSPi device, for thousands of
+// independent device instances, sm_100a.
 //
 // Reference: process_audio_packet(), firmware/DSPi/usb_audio.c:500-1317 — float pipeline :560-967,
 // single-core branch :874-960; crossfeed.c:132-156; leveller.c:148-262; pdm_generator.c:351-397.
@@ -7,19 +7,28 @@
 // crossfeed (+ input peaks) -> matrix -> per-output EQ -> gain x volume -> delay -> peaks ->
 // 24-bit words / delta-sigma PDM.
 //
-// Three kernels per call, all instance-parallel (no instance ever talks to another):
-//   chain_front_kernel  warp = 16 instances x {L, R}: lanes 0-15 carry the left channel, lanes
-//                       16-31 the right channel of the same instances; the stereo-linked leveller
-//                       and the crossfeed L<->R mix exchange values with __shfl_xor(.., 16).
-//                       Writes the two master signals to a frame-major scratch.
-//   chain_out_kernel    warp = one output index x 32 instances: matrix mix, 10-band EQ (EqBank,
-//                       same register-resident cascade as eq_f32.cu), gain, delay ring in HBM,
-//                       peak/clip metering, float -> 24-bit conversion; the sub output leaves
-//                       Q28 samples for the modulator.
-//   chain_pdm_kernel    one instance per lane: 256x oversampled 2nd-order error-feedback
-//                       delta-sigma with the noise-shaped xorshift32 dither, 8 words per frame.
-// All per-instance parameters and states are SoA arrays with the instance index innermost, so a
-// warp touches consecutive addresses.
+// The chain is feed-forward between stages (nothing downstream feeds an upstream stage), so a call is
+// run stage by stage over whole slices of packets instead of packet by packet:
+//
+//   chain_pre_kernel      lane = instance: PCM unpack, preamp, the two loudness shelves; results leave
+//                         through a shared-memory transpose as ROWS [2 N][frames] (row = side * N + inst)
+//   K1 (eq_f32_kernel.cuh) the 10-band master EQ over those rows — the same TMA-fed packed-FFMA2 kernel
+//                         (and run-time specialisation) as the EQ engine, not a second implementation
+//   chain_post_kernel     warp = 16 instances x {L, R}: per-packet leveller (stereo-linked, 480-sample
+//                         look-ahead ring), input peaks, crossfeed; L <-> R exchange by __shfl_xor(.., 16)
+//   chain_mix_kernel      lane = frame: the 2 x 9 matrix, writes output ROWS [9 N][frames]
+//   K1                    per-output EQ over the 9 N rows (muted / disabled rows are masked out)
+//   chain_outpost_kernel  lane = frame, warp = (instance, packet): gain, delay, peak/clip metering,
+//                         float -> 24-bit S/PDIF pairs (coalesced 8-byte stores), Q28 for the modulator.
+//                         A delayed sample that lies inside the current call is read from the output
+//                         rows; only older history comes from the delay ring in HBM.
+//   chain_ring_kernel     once per call: the last <= 4096 post-gain samples go into the rings
+//   chain_pdm_kernel      one instance per lane: 256x oversampled 2nd-order delta-sigma (chain_pdm.cuh)
+//
+// Everything with a serial recurrence but little arithmetic keeps lane = instance; everything without
+// one runs lane = frame, fully coalesced; the EQ — 90 % of the arithmetic — runs in the kernel that is
+// tuned against the roofline.  All per-instance parameters and states are SoA arrays with the instance
+// index innermost.
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -28,27 +37,24 @@
 #include <vector>
 
 #include "eq_kernels.cuh"
-#include "eq_core.cuh"
 #include "chain_pdm.cuh"
 #include "chain_streams.cuh"
 
 namespace dspi {
 namespace {
 
-using namespace core;
-
 constexpr int kOuts = DSPI_CHAIN_OUTPUTS;
 constexpr int kRoles = DSPI_CHAIN_EQ_CHANNELS;
 constexpr int kMaxDelay = DSPI_CHAIN_MAX_DELAY;
 constexpr int kLa = DSPI_LA_SAMPLES;
 constexpr int kPkt = DSPI_PACKET_MAX;
+constexpr int kXs = 33;                           // shared-memory column stride: conflict-free for lane = instance AND lane = frame
 
 enum : uint8_t { F_BYPASS_MASTER = 1, F_LOUD = 2, F_XFEED = 4, F_LEV = 8, F_LOOKAHEAD = 16, F_ANY_DELAY = 32, F_SUB_ON = 64 };
 enum : uint8_t { O_ENABLED = 1, O_MUTE = 2, O_PAIR_OFF = 4 };
 
 struct ChainDev {
-    uint32_t N, N_pad, nb, max_frames;
-    float *coef; uint64_t *modes;                 // packed EQ store, channel = role * N_pad + instance
+    uint32_t N, N_pad, nb, max_frames, ldF;       // ldF: row stride of mrow / orow / subq (frames, multiple of 4)
     float *preamp;                                // [2][N_pad]
     uint8_t *flags;                               // [N_pad] F_*
     float *loud_c; float *loud_st; uint8_t *loud_byp;   // [2 j][6][N_pad], [2 side][2 j][2][N_pad], [N_pad] bit j
@@ -58,7 +64,10 @@ struct ChainDev {
     float *dline; uint32_t *widx_in, *widx_out;   // [9][N_pad][4096], [N_pad]
     int32_t *pdm;                                 // [9][N_pad] err1 err2 x1 x2 y1 y2 err_acc rng fade_in_pos
     uint16_t *peaks; uint16_t *clip;              // [11][N_pad], [N_pad]
-    float *master; int32_t *subq;                 // [2][max_frames][N_pad], [max_frames][N_pad]
+    float *mrow;                                  // [2 N_pad][ldF] master rows, row = side * N_pad + inst
+    float *orow;                                  // [9 N_pad][ldF] output rows, row = o * N_pad + inst
+    int32_t *subq;                                // [N_pad][ldF] Q28 sub samples for the modulator
+    uint8_t *skip_m, *skip_o;                     // [2 N_pad], [9 N_pad]: rows whose EQ is frozen (K1 skip mask)
 };
 
 // a*b + c, c - a*b in the flavour's rounding (scalar: negation is free)
@@ -71,35 +80,6 @@ template <bool FUSED> __device__ __forceinline__ float fnm(float a, float b, flo
 {
     if (FUSED) return __fmaf_rn(-a, b, c);
     return __fadd_rn(c, -__fmul_rn(a, b));
-}
-
-__device__ __forceinline__ const float *eq_base(const ChainDev &d, uint32_t role, uint32_t inst)
-{
-    const uint32_t ch = role * d.N_pad + inst;
-    return d.coef + (size_t)(ch >> 5) * kMaxBands * 8 * 32 + (ch & 31);
-}
-
-// run one register tile through the bank unless this lane must skip it (state then stays frozen:
-// usb_audio.c:721-728 bypass_master_eq, :879-884 muted / disabled outputs)
-template <bool FUSED, int NB>
-__device__ __forceinline__ void bank_run_masked(EqBank<float, FUSED, NB> &bank, float (&x)[kSub], int nvalid, bool skip)
-{
-    if (!__any_sync(0xffffffffu, skip)) {
-        bank.run(x, nvalid, 0.0f);
-        return;
-    }
-    float keep_x[kSub], keep_s[NB][2];
-#pragma unroll
-    for (int i = 0; i < kSub; i++) keep_x[i] = x[i];
-#pragma unroll
-    for (int b = 0; b < NB; b++) { keep_s[b][0] = bank.st[b][0]; keep_s[b][1] = bank.st[b][1]; }
-    bank.run(x, nvalid, 0.0f);
-    if (skip) {
-#pragma unroll
-        for (int i = 0; i < kSub; i++) x[i] = keep_x[i];
-#pragma unroll
-        for (int b = 0; b < NB; b++) { bank.st[b][0] = keep_s[b][0]; bank.st[b][1] = keep_s[b][1]; }
-    }
 }
 
 // leveller.c:124-139
@@ -116,48 +96,156 @@ __device__ __forceinline__ float gain_computer(float x_db, float threshold, floa
 }
 
 // ---------------------------------------------------------------------------------------------
-// front: unpack + preamp, loudness, master EQ, leveller, crossfeed, input peaks
+// pre: PCM unpack + preamp (usb_audio.c:591-686), loudness shelves (:689-718) -> master rows
 // ---------------------------------------------------------------------------------------------
-template <bool FUSED, int NB>
-__global__ void __launch_bounds__(128, 1)
-chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F)
+template <bool FUSED>
+__global__ void __launch_bounds__(64)
+chain_pre_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t f_begin, uint32_t f_end, uint32_t F)
 {
-    extern __shared__ float smem[];                       // [warps][kPkt][32] packet column + the same again for look-ahead reads
+    __shared__ float tile_s[2][2][32][kXs];
+    __shared__ uint32_t pcm_s[2][2][32][49];              // per warp, double-buffered: 32 instances x 32 frames x <= 6 bytes (rows padded to 49 words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t side = lane >> 4;
-    const uint32_t inst = (blockIdx.x * (blockDim.x >> 5) + warp) * 16 + (lane & 15);
-    if ((blockIdx.x * (blockDim.x >> 5) + warp) * 16 >= d.N_pad) return;
+    const uint32_t inst0 = (blockIdx.x * 2 + warp) * 32;
+    if (inst0 >= d.N_pad) return;
+    const uint32_t inst = inst0 + lane;
     const bool live = inst < d.N;
-    float *xs = smem + (size_t)warp * kPkt * 32 + lane;   // xs[t * 32]
-    float *hs = smem + (size_t)(blockDim.x >> 5) * kPkt * 32 + (size_t)warp * kPkt * 32 + lane;   // held look-ahead samples
     const uint32_t Np = d.N_pad;
+    float (*tile)[32][kXs] = tile_s[warp];
 
-    const uint8_t flags = d.flags[inst];
-    const bool loud_on = flags & F_LOUD, lev_on = flags & F_LEV, xf_on = flags & F_XFEED;
-    const bool skip_master = flags & F_BYPASS_MASTER;
-    const bool lookahead = flags & F_LOOKAHEAD;
-    const float preamp = d.preamp[side * Np + inst];
-
-    EqBank<float, FUSED, NB> bank;
-    float *my_coef = const_cast<float *>(eq_base(d, side, inst));
-    {
-        const uint64_t *mp[1] = { d.modes + side * Np + inst };
-        bank.load(my_coef, mp, d.nb);
-    }
-    // loudness: 2 general-mix SVF shelves per side (usb_audio.c:689-718)
-    float lc[2][6], ls[2][2];
+    const bool loud_on = d.flags[inst] & F_LOUD;
     const uint8_t loud_byp = d.loud_byp[inst];
+    float lc[2][6], ls[2][2][2], gain_in[2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
 #pragma unroll
         for (int k = 0; k < 6; k++) lc[j][k] = d.loud_c[(j * 6 + k) * Np + inst];
-        ls[j][0] = d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst];
-        ls[j][1] = d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            ls[side][j][0] = d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst];
+            ls[side][j][1] = d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst];
+        }
     }
-    // crossfeed (crossfeed.c:132-156): this lane owns its side's lowpass / all-pass state
+    const uint32_t bpf = bit_depth == 24 ? 6u : 4u;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const float preamp = d.preamp[side * Np + inst];
+        gain_in[side] = bit_depth == 24 ? __fmul_rn(1.0f / 8388608.0f, preamp)       // usb_audio.c:601-603
+                                        : __fmul_rn(1.0f / 32768.0f, preamp);         // :680-681
+    }
+    // Each instance's packet stream is contiguous ([inst][F] frames of bpf bytes); when every tile starts on
+    // a 4-byte boundary the warp fetches the 32 tiles of its instances with coalesced word loads into shared
+    // memory and every lane then decodes its own instance from there, otherwise lanes read their bytes directly.
+    const bool words_ok = ((reinterpret_cast<uintptr_t>(pcm) | ((size_t)F * bpf) | ((size_t)f_begin * bpf)) & 3u) == 0;
+    const uint8_t *my_pcm = pcm + (size_t)inst * F * bpf;
+    const uint32_t n_inst = min(32u, d.N > inst0 ? d.N - inst0 : 0u);
+    // asynchronous fetch of the tile starting at frame f0 into buffer `buf` (one commit group per call).  A last
+    // word may run <= 2 bytes past a ragged tile: still inside the PCM buffer, because the very end of the
+    // buffer is word-aligned (F * bpf is) and so is every tile start.
+    auto fetch = [&](uint32_t f0, int buf) {
+        if (words_ok && f0 < f_end) {
+            const uint32_t nwords = (min(32u, f_end - f0) * bpf + 3) / 4;
+            for (uint32_t i = 0; i < n_inst; i++) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(pcm + ((size_t)(inst0 + i) * F + f0) * bpf);
+                for (uint32_t w = lane; w < nwords; w += 32) cp_async_4(&pcm_s[warp][buf][i][w], src + w);
+            }
+        }
+        cp_async_commit();
+    };
+    fetch(f_begin, 0);
+
+    int buf = 0;
+    for (uint32_t f0 = f_begin; f0 < f_end; f0 += 32, buf ^= 1) {
+        const uint32_t nv = min(32u, f_end - f0);
+        const uint8_t *tile_bytes = my_pcm + (size_t)f0 * bpf;
+        fetch(f0 + 32, buf ^ 1);                          // next tile streams in behind this tile's arithmetic
+        if (words_ok) {
+            cp_async_wait<1>();
+            __syncwarp();
+            tile_bytes = reinterpret_cast<const uint8_t *>(pcm_s[warp][buf][lane]);
+        }
+        for (uint32_t t = 0; t < nv; t++) {
+            const uint8_t *q = tile_bytes + (size_t)t * bpf;
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                int32_t s = 0;
+                if (live) {
+                    if (bit_depth == 24) {
+                        const uint8_t *b = q + side * 3;
+                        s = ((int32_t)((uint32_t)b[2] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[0] << 8)) >> 8;
+                    } else {
+                        const uint8_t *b = q + side * 2;
+                        s = (int16_t)((uint16_t)b[0] | (uint16_t)b[1] << 8);
+                    }
+                }
+                float v = __fmul_rn((float)s, gain_in[side]);                // :645-648 / :683-684
+                if (loud_on) {
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        if ((loud_byp >> j) & 1) continue;
+                        float &s0 = ls[side][j][0], &s1 = ls[side][j][1];
+                        const float v3 = __fadd_rn(v, -s1);
+                        const float pp = __fmul_rn(lc[j][1], v3);
+                        float t2, v1, v2;
+                        if (FUSED) {
+                            t2 = __fmaf_rn(lc[j][1], s0, s1);
+                            v1 = __fmaf_rn(lc[j][0], s0, pp);
+                            v2 = __fmaf_rn(lc[j][2], v3, t2);
+                        } else {
+                            t2 = __fadd_rn(s1, __fmul_rn(lc[j][1], s0));
+                            v1 = __fadd_rn(__fmul_rn(lc[j][0], s0), pp);
+                            v2 = __fadd_rn(t2, __fmul_rn(lc[j][2], v3));
+                        }
+                        s0 = __fmaf_rn(2.0f, v1, -s0);
+                        s1 = __fmaf_rn(2.0f, v2, -s1);
+                        v = fm<FUSED>(lc[j][5], v2, fm<FUSED>(lc[j][3], v, __fmul_rn(lc[j][4], v1)));   // :702
+                    }
+                }
+                tile[side][t][lane] = v;
+            }
+        }
+        __syncwarp();
+        // transpose out: lane = frame, one coalesced 128-byte store per (side, instance) row
+        if ((uint32_t)lane < nv) {
+#pragma unroll 8
+            for (int r = 0; r < 64; r++) {
+                const int side = r >> 5, i = r & 31;
+                d.mrow[((size_t)side * Np + inst0 + i) * d.ldF + f0 + lane] = tile[side][lane][i];
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst] = ls[side][j][0];
+            d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst] = ls[side][j][1];
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// post: leveller (leveller.c:148-262), input peaks, crossfeed (crossfeed.c:132-156), packet by packet
+// ---------------------------------------------------------------------------------------------
+template <bool FUSED>
+__global__ void __launch_bounds__(128)
+chain_post_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
+{
+    extern __shared__ float smem[];                       // per warp: packet columns [fpp][33] + look-ahead reads [fpp][33]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t side = lane >> 4;
+    const uint32_t inst16 = (blockIdx.x * (blockDim.x >> 5) + warp) * 16;
+    if (inst16 >= d.N_pad) return;
+    const uint32_t inst = inst16 + (lane & 15);
+    const uint32_t Np = d.N_pad;
+    float *xw = smem + (size_t)warp * 2 * fpp * kXs;      // xw[t * 33 + r]: column r of this warp
+    float *xs = xw + lane;                                // own column
+    float *hs = xw + (size_t)fpp * kXs + lane;            // held look-ahead samples, own column
+
+    const uint8_t flags = d.flags[inst];
+    const bool lev_on = flags & F_LEV, xf_on = flags & F_XFEED, lookahead = flags & F_LOOKAHEAD;
+    // crossfeed: this lane owns its side's lowpass / all-pass state
     const float xf_a0 = d.xf[0 * Np + inst], xf_b1 = d.xf[1 * Np + inst], xf_ap = d.xf[4 * Np + inst];
     float xf_lp = d.xf[(2 + side) * Np + inst], xf_as = d.xf[(5 + side) * Np + inst];
-    // leveller (leveller.c:148-262)
     float lvc[9];
 #pragma unroll
     for (int k = 0; k < 9; k++) lvc[k] = d.lev_c[k * Np + inst];
@@ -166,83 +254,28 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
     uint32_t la_idx = d.lev_idx[inst];
     float *la_buf = d.lev_la + (size_t)side * kLa * Np + inst;
 
-    const uint32_t bpf = bit_depth == 24 ? 6u : 4u;
-    const uint8_t *my_pcm = pcm + ((size_t)inst * F) * bpf + side * (bpf / 2);
-    float gain_in;
-    if (bit_depth == 24) gain_in = __fmul_rn(1.0f / 8388608.0f, preamp);     // usb_audio.c:601-603
-    else gain_in = __fmul_rn(1.0f / 32768.0f, preamp);                       // :680-681
-
     float peak_in = 0.0f;
     uint16_t clip = 0;
-    const uint32_t f_end = (p0 + n_packets) * fpp;
     for (uint32_t p = p0; p < p0 + n_packets; p++) {
         const uint32_t f0 = p * fpp;
-        // The leveller's look-ahead ring is read one slot per sample, each read just before that slot is
-        // overwritten (leveller.c:231-237), and a packet (<= 192 frames) never laps the 480-slot ring:
-        // all of this packet's reads can be issued now, as asynchronous copies into shared memory that
-        // complete behind passes 1-2, instead of one exposed HBM round trip per sample.
+        // The look-ahead ring is read one slot per sample, each read just before that slot is overwritten
+        // (leveller.c:231-237), and a packet (<= 192 frames) never laps the 480-slot ring: all of this
+        // packet's reads are issued now as asynchronous copies, together with the packet itself.
         if (lev_on && lookahead) {
             uint32_t idx = la_idx;
             for (uint32_t i = 0; i < fpp; i++) {
-                cp_async_4(hs + i * 32, la_buf + (size_t)idx * Np);
+                cp_async_4(hs + i * kXs, la_buf + (size_t)idx * Np);
                 if (++idx >= (uint32_t)kLa) idx = 0;
             }
         }
-        cp_async_commit();
-        // ---- PASS 1 + loudness + PASS 2 (master EQ), register tiles of 8 ----
-        for (uint32_t t0 = 0; t0 < fpp; t0 += kSub) {
-            const int nvalid = min((int)kSub, (int)(fpp - t0));
-            float x[kSub];
-            if (live) {                                    // next tile's PCM bytes (a private 6 B/frame stream per lane) towards L1
-                const uint32_t fn = f0 + t0 + kSub;
-                if (fn < f_end) {
-                    prefetch_l1(my_pcm + (size_t)fn * bpf);
-                    prefetch_l1(my_pcm + (size_t)(min(fn + (uint32_t)kSub, f_end) - 1) * bpf);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < kSub; i++) {
-                int32_t s = 0;
-                if (live && i < nvalid) {
-                    const uint8_t *q = my_pcm + (size_t)(f0 + t0 + i) * bpf;
-                    if (bit_depth == 24) s = ((int32_t)((uint32_t)q[2] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[0] << 8)) >> 8;
-                    else s = (int16_t)((uint16_t)q[0] | (uint16_t)q[1] << 8);
-                }
-                x[i] = __fmul_rn((float)s, gain_in);                         // :645-648 / :683-684
-            }
-            if (loud_on) {
-#pragma unroll
-                for (int i = 0; i < kSub; i++) {
-                    if (i < nvalid) {
-                        float v = x[i];
-#pragma unroll
-                        for (int j = 0; j < 2; j++) {
-                            if ((loud_byp >> j) & 1) continue;
-                            const float v3 = __fadd_rn(v, -ls[j][1]);
-                            const float pp = __fmul_rn(lc[j][1], v3);
-                            float t, v1, v2;
-                            if (FUSED) {
-                                t = __fmaf_rn(lc[j][1], ls[j][0], ls[j][1]);
-                                v1 = __fmaf_rn(lc[j][0], ls[j][0], pp);
-                                v2 = __fmaf_rn(lc[j][2], v3, t);
-                            } else {
-                                t = __fadd_rn(ls[j][1], __fmul_rn(lc[j][1], ls[j][0]));
-                                v1 = __fadd_rn(__fmul_rn(lc[j][0], ls[j][0]), pp);
-                                v2 = __fadd_rn(t, __fmul_rn(lc[j][2], v3));
-                            }
-                            ls[j][0] = __fmaf_rn(2.0f, v1, -ls[j][0]);
-                            ls[j][1] = __fmaf_rn(2.0f, v2, -ls[j][1]);
-                            v = fm<FUSED>(lc[j][5], v2, fm<FUSED>(lc[j][3], v, __fmul_rn(lc[j][4], v1)));   // :702
-                        }
-                        x[i] = v;
-                    }
-                }
-            }
-            bank_run_masked<FUSED, NB>(bank, x, nvalid, skip_master);
-#pragma unroll
-            for (int i = 0; i < kSub; i++)
-                if (i < nvalid) xs[(t0 + i) * 32] = x[i];
+        // packet in: lane = frame, coalesced row reads, transposed into lane-private columns (asynchronous
+        // copies again: 32 rows x fpp/32 independent requests in flight instead of one load-store pair at a time)
+        for (int r = 0; r < 32; r++) {
+            const float *row = d.mrow + ((size_t)(r >> 4) * Np + inst16 + (r & 15)) * d.ldF + f0;
+            for (uint32_t t = lane; t < fpp; t += 32) cp_async_4(xw + t * kXs + r, row + t);
         }
+        cp_async_commit();
+        cp_async_wait_all();
         __syncwarp();
 
         // ---- PASS 2.5: leveller ----
@@ -250,7 +283,7 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
             const float a_rms = lvc[0], one_minus = __fadd_rn(1.0f, -a_rms);
             float e = env;
             for (uint32_t i = 0; i < fpp; i++) {                             // leveller.c:161-166
-                const float s = xs[i * 32];
+                const float s = xs[i * kXs];
                 e = fm<FUSED>(a_rms, e, __fmul_rn(one_minus, __fmul_rn(s, s)));
             }
             if (e < 1e-30f) e = 0.0f;                                        // :169-170
@@ -275,11 +308,10 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
             float gain, gain_step;
             if (fpp == 1) { gain = new_gain; gain_step = 0.0f; }
             else { gain_step = __fdiv_rn(__fadd_rn(new_gain, -prev_for_ramp), (float)(fpp - 1)); gain = prev_for_ramp; }
-            cp_async_wait_all();                                             // this lane's look-ahead reads have landed
             for (uint32_t i = 0; i < fpp; i++) {                             // :228-259
-                float o = xs[i * 32];
+                float o = xs[i * kXs];
                 if (lev_on && lookahead) {
-                    const float held = hs[i * 32];
+                    const float held = hs[i * kXs];
                     la_buf[(size_t)la_idx * Np] = o;
                     o = held;
                     la_idx++;
@@ -295,7 +327,7 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
                     const float max_g = __fdiv_rn(0.70795f, peak);
                     if (max_g < g) g = (max_g > 1.0f) ? max_g : 1.0f;
                 }
-                if (lev_on) xs[i * 32] = __fmul_rn(o, g);
+                if (lev_on) xs[i * kXs] = __fmul_rn(o, g);
                 gain = __fadd_rn(gain, gain_step);
             }
             if (lev_on) {
@@ -308,9 +340,8 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
 
         // ---- PASS 3: input peaks, then crossfeed (usb_audio.c:741-749) ----
         float pk = 0.0f;
-        float *mout = d.master + ((size_t)side * d.max_frames + f0) * Np + inst;
         for (uint32_t i = 0; i < fpp; i++) {
-            float v = xs[i * 32];
+            float v = xs[i * kXs];
             const float a = fabsf(v);
             if (a > pk) pk = a;
             float lp = 0.0f, ap = 0.0f;
@@ -322,20 +353,21 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
             }
             const float ap_other = __shfl_xor_sync(0xffffffffu, ap, 16);
             if (xf_on) v = __fadd_rn(__fadd_rn(v, -lp), ap_other);           // :154-155
-            mout[(size_t)i * Np] = v;
+            xs[i * kXs] = v;
         }
         peak_in = pk;                                                        // peaks describe the last packet
         if (pk > 1.001f) clip |= (uint16_t)(1u << side);                     // config.h:53
         __syncwarp();
+        // packet out: back into the same rows, coalesced
+        for (uint32_t t = lane; t < fpp; t += 32) {
+#pragma unroll 8
+            for (int r = 0; r < 32; r++)
+                d.mrow[((size_t)(r >> 4) * Np + inst16 + (r & 15)) * d.ldF + f0 + t] = xw[t * kXs + r];
+        }
+        __syncwarp();
     }
 
     // ---- state back ----
-    bank.store(my_coef);
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-        d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst] = ls[j][0];
-        d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst] = ls[j][1];
-    }
     d.xf[(2 + side) * Np + inst] = xf_lp;
     d.xf[(5 + side) * Np + inst] = xf_as;
     d.lev_s[side * Np + inst] = env;
@@ -346,214 +378,217 @@ chain_front_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_dep
         d.lev_idx[inst] = la_idx;
     }
     d.peaks[side * Np + inst] = (uint16_t)__fmul_rn(fminf(1.0f, peak_in), 32767.0f);    // usb_audio.c:963-964
+    // clip_flags bits 0/1: the two sides of one instance sit in lanes l and l+16; two instances share a 32-bit word
     const uint16_t clip_other = (uint16_t)__shfl_xor_sync(0xffffffffu, (uint32_t)clip, 16);
-    if (side == 0) atomicOr(reinterpret_cast<unsigned int *>(d.clip + (inst & ~1u)), (unsigned int)(clip | clip_other) << (16 * (inst & 1)));
+    if (side == 0 && (clip | clip_other)) atomicOr(reinterpret_cast<unsigned int *>(d.clip + (inst & ~1u)), (unsigned int)(clip | clip_other) << (16 * (inst & 1)));
 }
 
 // ---------------------------------------------------------------------------------------------
-// outputs: matrix, per-output EQ, gain, delay, peaks, 24-bit conversion / Q28 for the modulator
+// matrix mix (usb_audio.c:753-779): lane = frame
 // ---------------------------------------------------------------------------------------------
-template <bool FUSED, int NB>
-__global__ void __launch_bounds__(128, 3)
-chain_out_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F, int32_t *__restrict__ spdif_out)
+template <bool FUSED>
+__global__ void __launch_bounds__(256)
+chain_mix_kernel(ChainDev d, uint32_t f_begin, uint32_t f_end)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + warp;
-    const uint32_t groups = d.N_pad / 32;
-    if (wid >= groups * kOuts) return;
-    const uint32_t o = wid / groups;                         // output index: warp-uniform
-    const uint32_t inst = (wid % groups) * 32 + lane;
-    const bool live = inst < d.N;
+    const int lane = threadIdx.x & 31;
+    constexpr int kB = 4;                                  // frames per lane per unit: kB independent loads in flight
+    const uint32_t n_tiles = (f_end - f_begin + 32 * kB - 1) / (32 * kB);
+    const uint64_t units = (uint64_t)d.N * n_tiles;
     const uint32_t Np = d.N_pad;
-
-    const uint8_t of = d.o_flags[o * Np + inst];
-    const bool enabled = of & O_ENABLED, mute = of & O_MUTE, pair_off = of & O_PAIR_OFF;
-    const float gl = d.o_gl[o * Np + inst], gr = d.o_gr[o * Np + inst], gain = d.o_gain[o * Np + inst];
-    const int32_t dly = d.o_dly[o * Np + inst];
-    const bool delay_on = (d.flags[inst] & F_ANY_DELAY) && dly > 0;          // usb_audio.c:898-901
-    const bool any_delay = d.flags[inst] & F_ANY_DELAY;
-    const bool ring_early = delay_on && dly >= kSub && dly < kMaxDelay;
-    const uint32_t f_end = (p0 + n_packets) * fpp;
-    uint32_t widx = d.widx_in[inst];
-    float *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;     // one contiguous ring per (output, instance)
-
-    EqBank<float, FUSED, NB> bank;
-    float *my_coef = const_cast<float *>(eq_base(d, 2 + o, inst));
-    {
-        const uint64_t *mp[1] = { d.modes + (2 + o) * Np + inst };
-        bank.load(my_coef, mp, d.nb);
-    }
-    const bool skip_eq = !enabled || mute;                                   // :878-884
-    const int mixcase = !enabled ? 0 : (gl != 0.0f && gr != 0.0f) ? 3 : (gl != 0.0f) ? 1 : (gr != 0.0f) ? 2 : 0;   // :767-778
-
-    // The master L/R rows a tile needs are staged through shared memory by asynchronous copies issued two
-    // tiles ahead (each lane fetches its own instance's samples, so no warp synchronisation is needed):
-    // the load latency (L2 / HBM) overlaps the EQ arithmetic of the tiles in between.
-    constexpr int kLrStages = 3;
-    __shared__ float lr_stage[4][kLrStages][2][kSub][32];
-    float *lr = &lr_stage[warp][0][0][0][lane];
-    const uint32_t tpp = (fpp + kSub - 1) / kSub, n_tiles = n_packets * tpp;
-    auto issue_lr = [&](uint32_t n) {
-        if (n < n_tiles) {
-            const uint32_t pn = p0 + n / tpp, tt = (n % tpp) * kSub;
-            float *dst = lr + (n % kLrStages) * (2 * kSub * 32);
-            const float *src = d.master + ((size_t)pn * fpp + tt) * Np + inst;
+    for (uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t inst = (uint32_t)(u / n_tiles), tile = (uint32_t)(u % n_tiles);
+        const uint32_t fbase = f_begin + tile * 32 * kB + lane;
+        float l[kB], r[kB];
 #pragma unroll
-            for (int i = 0; i < kSub; i++) {
-                if (tt + i < fpp) {
-                    if (mixcase & 1) cp_async_4(dst + i * 32, src + (size_t)i * Np);
-                    if (mixcase & 2) cp_async_4(dst + (kSub + i) * 32, src + ((size_t)d.max_frames + i) * Np);
-                }
-            }
+        for (int j = 0; j < kB; j++) {
+            const uint32_t f = fbase + 32 * j;
+            l[j] = f < f_end ? d.mrow[(size_t)inst * d.ldF + f] : 0.0f;
+            r[j] = f < f_end ? d.mrow[((size_t)Np + inst) * d.ldF + f] : 0.0f;
         }
-        cp_async_commit();
-    };
 #pragma unroll
-    for (int n = 0; n < kLrStages - 1; n++) issue_lr(n);
-    uint32_t tile_n = 0;
-
-    float peak_last = 0.0f;
-    uint16_t clip = 0;
-    const bool is_sub = o == kOuts - 1;
-    int32_t *my_spdif = nullptr;
-    if (!is_sub && spdif_out && live) my_spdif = spdif_out + (((size_t)inst * 4 + (o >> 1)) * F) * 2 + (o & 1);
-
-    for (uint32_t p = p0; p < p0 + n_packets; p++) {
-        const uint32_t f0 = p * fpp;
-        float pk = 0.0f;
-        uint32_t w = widx;
-        for (uint32_t t0 = 0; t0 < fpp; t0 += kSub) {
-            const int nvalid = min((int)kSub, (int)(fpp - t0));
-            float x[kSub];
-            issue_lr(tile_n + kLrStages - 1);                                // master L/R of the tile two ahead
-            cp_async_wait<kLrStages - 1>();                                  // ... and this tile's have landed
-            const float *cur = lr + (tile_n % kLrStages) * (2 * kSub * 32);
-            tile_n++;
-            // Delay ring (:902-909 is write-then-read per sample).  For kSub <= dly < MAX the slots this
-            // tile reads were written by earlier tiles (and the slots it writes are not read in it), so
-            // the reads are issued NOW and their HBM latency hides behind the matrix + EQ arithmetic.
-            float rd[kSub];
-            if (ring_early) {
+        for (int o = 0; o < kOuts; o++) {
+            const bool enabled = d.o_flags[o * Np + inst] & O_ENABLED;
+            const float gl = d.o_gl[o * Np + inst], gr = d.o_gr[o * Np + inst];
+            const int mixcase = !enabled ? 0 : (gl != 0.0f && gr != 0.0f) ? 3 : (gl != 0.0f) ? 1 : (gr != 0.0f) ? 2 : 0;   // :767-778
 #pragma unroll
-                for (int i = 0; i < kSub; i++)
-                    if (i < nvalid) rd[i] = ring[(w + i - (uint32_t)dly) & (kMaxDelay - 1)];
-            }
-#pragma unroll
-            for (int i = 0; i < kSub; i++) {
-                float l = 0.0f, r = 0.0f;
-                if (i < nvalid) {
-                    if (mixcase & 1) l = cur[i * 32];
-                    if (mixcase & 2) r = cur[(kSub + i) * 32];
-                }
+            for (int j = 0; j < kB; j++) {
                 float v;
-                if (mixcase == 3) v = fm<FUSED>(l, gl, __fmul_rn(r, gr));    // :769
-                else if (mixcase == 1) v = __fmul_rn(l, gl);
-                else if (mixcase == 2) v = __fmul_rn(r, gr);
+                if (mixcase == 3) v = fm<FUSED>(l[j], gl, __fmul_rn(r[j], gr));          // :769
+                else if (mixcase == 1) v = __fmul_rn(l[j], gl);
+                else if (mixcase == 2) v = __fmul_rn(r[j], gr);
                 else v = 0.0f;
-                x[i] = v;
-            }
-            bank_run_masked<FUSED, NB>(bank, x, nvalid, skip_eq);
-#pragma unroll
-            for (int i = 0; i < kSub; i++) {
-                if (enabled) {                                               // :885-894
-                    if (gain == 0.0f) x[i] = 0.0f;
-                    else if (gain != 1.0f) x[i] = __fmul_rn(x[i], gain);
-                }
-            }
-            if (ring_early) {
-#pragma unroll
-                for (int i = 0; i < kSub; i++)
-                    if (i < nvalid) { ring[(w + i) & (kMaxDelay - 1)] = x[i]; x[i] = rd[i]; }
-            } else if (delay_on) {                                           // dly < kSub, or dly == MAX (aliases to 0, SURVEY a-10)
-                for (int i = 0; i < nvalid; i++) {
-                    ring[(w + i) & (kMaxDelay - 1)] = x[i];
-                    x[i] = ring[(w + i - (uint32_t)dly) & (kMaxDelay - 1)];
-                }
-            }
-            w = (w + nvalid) & (kMaxDelay - 1);
-#pragma unroll
-            for (int i = 0; i < kSub; i++) {
-                if (i >= nvalid) break;
-                const float v = x[i];
-                const float a = fabsf(v);
-                if (a > pk) pk = a;
-                if (is_sub) {
-                    if (enabled) d.subq[(size_t)(f0 + t0 + i) * Np + inst] = __float2int_rz(__fmul_rn(v, 268435456.0f));   // :953 (saturating)
-                } else if (my_spdif) {
-                    int32_t word = 0;
-                    if (!pair_off) {
-                        const float c = fmaxf(-1.0f, fminf(1.0f, v));       // :936-939
-                        word = __float2int_rz(__fmul_rn(c, 8388607.0f));
-                    }
-                    my_spdif[(size_t)(f0 + t0 + i) * 2] = word;
-                }
+                const uint32_t f = fbase + 32 * j;
+                if (f < f_end) d.orow[((size_t)o * Np + inst) * d.ldF + f] = v;
             }
         }
-        if (any_delay) widx = (widx + fpp) & (kMaxDelay - 1);               // :911
-        peak_last = pk;
-        if (pk > 1.001f && (!is_sub || enabled)) clip |= 1;
     }
-    bank.store(my_coef);
-    uint16_t pq = (uint16_t)__fmul_rn(fminf(1.0f, peak_last), 32767.0f);    // :921 / :950
-    if (is_sub && !enabled) pq = 0;                                          // :957
-    d.peaks[(2 + o) * Np + inst] = pq;
-    if (clip) atomicOr(reinterpret_cast<unsigned int *>(d.clip + (inst & ~1u)), (1u << (2 + o)) << (16 * (inst & 1)));
-    if (o == 0) d.widx_out[inst] = widx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// outputs after the EQ: gain (:885-894), delay (:898-912), peaks (:914-923), 24-bit / Q28 (:925-959)
+// ---------------------------------------------------------------------------------------------
+// post-gain sample of output row `o` (what the delay line stores)
+__device__ __forceinline__ float out_gain(float v, bool enabled, float gain)
+{
+    if (enabled) {
+        if (gain == 0.0f) v = 0.0f;
+        else if (gain != 1.0f) v = __fmul_rn(v, gain);
+    }
+    return v;
+}
+
+struct OutCfg {
+    bool enabled, pair_off, delay_on;
+    float gain;
+    uint32_t dl;                       // delay & (MAX - 1): MAX aliases to 0 (SURVEY a-10)
+    const float *row;                  // orow row of this (output, instance)
+    const float *ring;
+};
+
+__device__ __forceinline__ OutCfg out_cfg(const ChainDev &d, uint32_t o, uint32_t inst, bool any_delay)
+{
+    OutCfg c;
+    const uint32_t Np = d.N_pad;
+    const uint8_t of = d.o_flags[o * Np + inst];
+    const int32_t dly = d.o_dly[o * Np + inst];
+    c.enabled = of & O_ENABLED;
+    c.pair_off = of & O_PAIR_OFF;
+    c.gain = d.o_gain[o * Np + inst];
+    c.delay_on = any_delay && dly > 0;                                       // usb_audio.c:898-901
+    c.dl = (uint32_t)dly & (kMaxDelay - 1);
+    c.row = d.orow + ((size_t)o * Np + inst) * d.ldF;
+    c.ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;
+    return c;
+}
+
+// the sample output `c` emits at frame T of this call (T counted from the start of the call):
+// write-then-read per sample (:902-909) means frame T emits the post-gain sample of frame T - dl;
+// inside the call that sample is still in the output rows, before it only the ring has it
+__device__ __forceinline__ float out_sample(const OutCfg &c, uint32_t T, uint32_t widx0)
+{
+    if (!c.delay_on) return out_gain(c.row[T], c.enabled, c.gain);
+    if (T >= c.dl) return out_gain(c.row[T - c.dl], c.enabled, c.gain);
+    return c.ring[(widx0 + T - c.dl) & (kMaxDelay - 1)];
+}
+
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, v, s);
+        if (o > v) v = o;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+chain_outpost_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F, int32_t *__restrict__ spdif_out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t units = (uint64_t)d.N * n_packets;
+    const uint32_t Np = d.N_pad;
+    for (uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t inst = (uint32_t)(u / n_packets), p = p0 + (uint32_t)(u % n_packets);
+        const uint32_t f0 = p * fpp;
+        const bool last = p == p0 + n_packets - 1;
+        const bool any_delay = d.flags[inst] & F_ANY_DELAY;
+        const uint32_t widx0 = d.widx_in[inst];
+        unsigned int clip = 0;
+        for (int k = 0; k <= 4; k++) {                                        // four S/PDIF pairs, then the sub alone
+            const bool is_sub = k == 4;
+            const uint32_t oa = 2 * k, ob = is_sub ? oa : oa + 1;
+            const OutCfg ca = out_cfg(d, oa, inst, any_delay), cb = out_cfg(d, ob, inst, any_delay);
+            float pka = 0.0f, pkb = 0.0f;
+            constexpr int kB = 4;                                            // independent loads in flight per lane
+            for (uint32_t tb = lane; tb < fpp; tb += 32 * kB) {
+                float xa[kB], xb[kB];
+#pragma unroll
+                for (int j = 0; j < kB; j++) {
+                    const uint32_t t = tb + 32 * j;
+                    xa[j] = t < fpp ? out_sample(ca, f0 + t, widx0) : 0.0f;
+                    xb[j] = (!is_sub && t < fpp) ? out_sample(cb, f0 + t, widx0) : 0.0f;
+                }
+#pragma unroll
+                for (int j = 0; j < kB; j++) {
+                    const uint32_t t = tb + 32 * j, T = f0 + t;
+                    if (t >= fpp) break;
+                    const float aa = fabsf(xa[j]), ab = fabsf(xb[j]);
+                    if (aa > pka) pka = aa;
+                    if (ab > pkb) pkb = ab;
+                    if (is_sub) {
+                        if (ca.enabled) d.subq[(size_t)inst * d.ldF + T] = __float2int_rz(__fmul_rn(xa[j], 268435456.0f));   // :953 (saturating)
+                    } else if (spdif_out) {
+                        int2 w = make_int2(0, 0);
+                        if (!ca.pair_off) {                                  // :930-939 (pair_off is a property of the pair)
+                            w.x = __float2int_rz(__fmul_rn(fmaxf(-1.0f, fminf(1.0f, xa[j])), 8388607.0f));
+                            w.y = __float2int_rz(__fmul_rn(fmaxf(-1.0f, fminf(1.0f, xb[j])), 8388607.0f));
+                        }
+                        *reinterpret_cast<int2 *>(spdif_out + (((size_t)inst * 4 + k) * F + T) * 2) = w;
+                    }
+                }
+            }
+            pka = warp_max(pka);
+            pkb = warp_max(pkb);
+            if (lane == 0) {
+                if (last) {
+                    uint16_t pq = (uint16_t)__fmul_rn(fminf(1.0f, pka), 32767.0f);              // :921 / :950
+                    if (is_sub && !ca.enabled) pq = 0;                                           // :957
+                    d.peaks[(2 + oa) * Np + inst] = pq;
+                    if (!is_sub) d.peaks[(2 + ob) * Np + inst] = (uint16_t)__fmul_rn(fminf(1.0f, pkb), 32767.0f);
+                }
+                if (pka > 1.001f && (!is_sub || ca.enabled)) clip |= 1u << (2 + oa);
+                if (!is_sub && pkb > 1.001f) clip |= 1u << (2 + ob);
+            }
+        }
+        if (lane == 0 && clip) atomicOr(reinterpret_cast<unsigned int *>(d.clip + (inst & ~1u)), clip << (16 * (inst & 1)));
+    }
+}
+
+// once per call, after every outpost launch of the call: the delay rings take the last <= 4096 post-gain
+// samples (older writes of this call would have been overwritten anyway), the shared write index advances
+__global__ void __launch_bounds__(256)
+chain_ring_kernel(ChainDev d, uint32_t F, uint32_t fpp)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t units = (uint64_t)d.N * kOuts;
+    const uint32_t Np = d.N_pad;
+    for (uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t inst = (uint32_t)(u / kOuts), o = (uint32_t)(u % kOuts);
+        const bool any_delay = d.flags[inst] & F_ANY_DELAY;
+        const uint32_t widx0 = d.widx_in[inst];
+        const OutCfg c = out_cfg(d, o, inst, any_delay);
+        if (c.delay_on) {                                                    // outputs without delay never touch their ring
+            float *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;
+            for (uint32_t T = (F > (uint32_t)kMaxDelay ? F - kMaxDelay : 0u) + lane; T < F; T += 32)
+                ring[(widx0 + T) & (kMaxDelay - 1)] = out_gain(c.row[T], c.enabled, c.gain);
+        }
+        if (o == 0 && lane == 0) d.widx_out[inst] = any_delay ? (widx0 + F) & (kMaxDelay - 1) : widx0;   // :911, once per packet
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // delta-sigma PDM (chain_pdm.cuh): one instance per lane
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(128)
 chain_pdm_kernel(ChainDev d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
     const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= d.N) return;
     if (!(d.flags[inst] & F_SUB_ON)) return;                                 // usb_audio.c:944
-    pdm_modulate_frames(d.pdm, d.subq, d.N_pad, inst, f_begin, f_end, F, pdm_out);
+    pdm_modulate_frames(d.pdm, d.subq + (size_t)inst * d.ldF, 1, d.N_pad, inst, f_begin, f_end, F, pdm_out);
 }
 
-// filters[][] of n instances (instance-major AoS) -> packed store with channel = role * N_pad + inst
-__global__ void chain_pack_kernel(const dspi_biquad_f32 *__restrict__ aos, uint32_t inst0, uint32_t n, ChainDev d)
+// filters[][] of n instances (instance-major AoS) <-> the mirrors of the two EQ engines (channel = role' * N_pad + inst)
+__global__ void chain_scatter_kernel(const dspi_biquad_f32 *__restrict__ aos, uint32_t inst0, uint32_t n, uint32_t Np, dspi_biquad_f32 *__restrict__ m_aos,
+                                     dspi_biquad_f32 *__restrict__ o_aos, int to_mirrors)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * kRoles) return;
-    const uint32_t inst = inst0 + i / kRoles, role = i % kRoles;
-    const uint32_t ch = role * d.N_pad + inst, g = ch >> 5, lane = ch & 31;
-    uint64_t mw = 0;
-    for (int b = 0; b < kMaxBands; b++) {
-        const dspi_biquad_f32 &q = aos[((size_t)inst * kRoles + role) * kMaxBands + b];
-        float v[8];
-        uint32_t mode;
-        if (q.bypass) mode = kModeBypass;
-        else if (!q.use_svf) mode = kModeTdf2;
-        else mode = q.svf_type == DSPI_FILTER_LOWPASS ? kModeSvfLP : q.svf_type == DSPI_FILTER_HIGHPASS ? kModeSvfHP
-                  : q.svf_type == DSPI_FILTER_PEAKING ? kModeSvfPK : kModeSvfSH;
-        if (q.use_svf && !q.bypass) {
-            v[0] = q.sva1; v[1] = q.sva2; v[2] = q.sva3; v[3] = q.svm0; v[4] = q.svm1; v[5] = q.svm2; v[6] = q.svic1eq; v[7] = q.svic2eq;
-        } else {
-            v[0] = q.b0; v[1] = q.b1; v[2] = q.b2; v[3] = -q.a1; v[4] = -q.a2; v[5] = 0.0f; v[6] = q.s1; v[7] = q.s2;
-        }
-        mw |= (uint64_t)mode << (4 * b);
-        for (int k = 0; k < 8; k++) d.coef[(((size_t)g * kMaxBands + b) * 8 + k) * 32 + lane] = v[k];
-    }
-    d.modes[ch] = mw;
-}
-
-__global__ void chain_unpack_kernel(dspi_biquad_f32 *__restrict__ aos, uint32_t inst0, uint32_t n, ChainDev d)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * kRoles) return;
-    const uint32_t inst = inst0 + i / kRoles, role = i % kRoles;
-    const uint32_t ch = role * d.N_pad + inst, g = ch >> 5, lane = ch & 31;
-    for (int b = 0; b < kMaxBands; b++) {
-        dspi_biquad_f32 &q = aos[((size_t)inst * kRoles + role) * kMaxBands + b];
-        if (q.bypass) continue;
-        const float s0 = d.coef[(((size_t)g * kMaxBands + b) * 8 + 6) * 32 + lane];
-        const float s1 = d.coef[(((size_t)g * kMaxBands + b) * 8 + 7) * 32 + lane];
-        if (q.use_svf) { q.svic1eq = s0; q.svic2eq = s1; }
-        else { q.s1 = s0; q.s2 = s1; }
-    }
+    if (i >= n * kRoles * kMaxBands) return;
+    const uint32_t b = i % kMaxBands, role = (i / kMaxBands) % kRoles, inst = inst0 + i / (kMaxBands * kRoles);
+    dspi_biquad_f32 *chain_q = const_cast<dspi_biquad_f32 *>(aos) + ((size_t)inst * kRoles + role) * kMaxBands + b;
+    dspi_biquad_f32 *eng_q = role < 2 ? m_aos + ((size_t)role * Np + inst) * kMaxBands + b : o_aos + ((size_t)(role - 2) * Np + inst) * kMaxBands + b;
+    if (to_mirrors) *eng_q = *chain_q;
+    else *chain_q = *eng_q;
 }
 
 __global__ void chain_status_kernel(ChainDev d, dspi_status *__restrict__ out)
@@ -597,6 +632,7 @@ struct dspi_chain {
     cudaStream_t stream;                  // the engine stream callers see; stages run on st.* between ev_begin and ev_done
     dspi::ChainStreams st;
     dspi_biquad_f32 *d_aos;          // [N_pad][11][12] instance-major mirror of filters[][]
+    dspi_eq *eq_m, *eq_o;            // K1 engines over the master rows (2 N_pad channels) and the output rows (9 N_pad)
     std::vector<void *> allocs;
     uint64_t launches;
     void *d_pcm; size_t pcm_bytes;   // host-path staging
@@ -646,35 +682,55 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
                  dspi_status *d_status)
 {
     const uint32_t F = n_packets * fpp;
-    auto front = dspi::chain_front_kernel<FUSED, 10>;
-    const size_t smem = (size_t)2 * 4 * dspi::kPkt * 32 * 4;      // packet column + look-ahead column per warp
-    static bool configured = false;
-    if (!configured) { CU_OK(cudaFuncSetAttribute(front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
-    // Stage pipeline over packet slices on three streams (chain_streams.cuh).
+    auto post = dspi::chain_post_kernel<FUSED>;
+    const size_t post_smem = (size_t)4 * 2 * fpp * dspi::kXs * 4;           // 4 warps x (packet + look-ahead columns)
+    static size_t post_smem_set = 0;
+    if (post_smem > post_smem_set) {
+        CU_OK(cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * 2 * dspi::kPkt * dspi::kXs * 4)));
+        post_smem_set = (size_t)4 * 2 * dspi::kPkt * dspi::kXs * 4;
+    }
+    // Stage pipeline over packet slices on three streams (chain_streams.cuh): front stages of slice
+    // i+1 overlap the output stages of slice i and the modulator of slice i-1.
     dspi::ChainStreams &st = c->st;
     const uint32_t n_slices = n_packets < (uint32_t)dspi::ChainStreams::kMaxSlices ? n_packets : (uint32_t)dspi::ChainStreams::kMaxSlices;
+    const ChainDev d = c->d;
+    const uint32_t n_sms = 148;
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
     CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t p0 = (uint32_t)((uint64_t)n_packets * sl / n_slices), p1 = (uint32_t)((uint64_t)n_packets * (sl + 1) / n_slices);
-        const ChainDev d = c->d;
-        const uint32_t fwarps = d.N_pad / 16, owarps = d.N_pad / 32 * dspi::kOuts;
-        front<<<(fwarps + 3) / 4, 128, smem, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, p0, p1 - p0, fpp, F);
+        const uint32_t fb = p0 * fpp, fe = p1 * fpp;
+        int rc;
+        // ---- front: unpack + loudness -> master EQ (K1) -> leveller + crossfeed
+        dspi::chain_pre_kernel<FUSED><<<(d.N_pad / 32 + 1) / 2, 64, 0, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, fb, fe, F);
+        CU_OK(cudaGetLastError());
+        if ((rc = dspi::eq_process_on(c->eq_m, d.mrow + fb, fe - fb, d.ldF, st.s_front)) != DSPI_OK) return rc;
+        post<<<(d.N_pad / 16 + 3) / 4, 128, post_smem, st.s_front>>>(d, p0, p1 - p0, fpp);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_front[sl], st.s_front));
+        // ---- outputs: matrix -> per-output EQ (K1) -> gain / delay / metering / conversion
         CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
-        dspi::chain_out_kernel<FUSED, 10><<<(owarps + 3) / 4, 128, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        dspi::chain_mix_kernel<FUSED><<<n_sms * 8, 256, 0, st.s_out>>>(d, fb, fe);
         CU_OK(cudaGetLastError());
-        std::swap(c->d.widx_in, c->d.widx_out);
+        if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
+        dspi::chain_outpost_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
+        // ---- modulator
         CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
-        dspi::chain_pdm_kernel<<<(d.N + 63) / 64, 64, 0, st.s_pdm>>>(d, p0 * fpp, p1 * fpp, F, d_pdm);
+        dspi::chain_pdm_kernel<<<(d.N + 127) / 128, 128, 0, st.s_pdm>>>(d, fb, fe, F, d_pdm);
         CU_OK(cudaGetLastError());
-        c->launches += 3;
+        c->launches += 5;
     }
+    dspi::chain_ring_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, F, fpp);     // after the last outpost launch (stream order)
+    CU_OK(cudaGetLastError());
+    c->launches++;
+    std::swap(c->d.widx_in, c->d.widx_out);
+    CU_OK(cudaEventRecord(st.ev_aux, st.s_out));                             // ring update done
+    CU_OK(cudaStreamWaitEvent(c->stream, st.ev_aux, 0));
     // the last modulator launch is ordered after every other stage launch of this call
     CU_OK(cudaEventRecord(st.ev_done, st.s_pdm));
-    CU_OK(cudaStreamWaitEvent(c->stream, st.ev_done, 0));         // later work on the engine stream sees all outputs
+    CU_OK(cudaStreamWaitEvent(c->stream, st.ev_done, 0));                    // later work on the engine stream sees all outputs
     if (d_status) {
         dspi::chain_status_kernel<<<(c->d.N + 127) / 128, 128, 0, c->stream>>>(c->d, d_status);
         CU_OK(cudaGetLastError());
@@ -703,6 +759,8 @@ int dspi_chain_destroy(dspi_chain *c)
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->st.destroy();
+    if (c->eq_m) dspi_eq_destroy(c->eq_m);
+    if (c->eq_o) dspi_eq_destroy(c->eq_o);
     for (void *p : c->allocs) cudaFree(p);
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_spdif) cudaFree(c->d_spdif);
@@ -731,6 +789,7 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     if (!c) return fail(DSPI_ENOMEM, "host allocation failed");
     c->stream = nullptr;
     c->st = dspi::ChainStreams();
+    c->eq_m = c->eq_o = nullptr;
     c->d_aos = nullptr; c->launches = 0; c->d_pcm = nullptr; c->pcm_bytes = 0; c->d_spdif = nullptr; c->spdif_bytes = 0;
     c->d_pdmout = nullptr; c->pdmout_bytes = 0; c->d_status = nullptr;
     c->desc = *desc;
@@ -740,13 +799,22 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     d.N_pad = (d.N + 31) / 32 * 32;
     d.nb = desc->n_bands;
     d.max_frames = desc->max_frames;
+    d.ldF = (d.max_frames + 3u) & ~3u;
     const size_t Np = d.N_pad;
+    {
+        dspi_eq_desc ed;
+        memset(&ed, 0, sizeof(ed));
+        ed.arith = desc->arith; ed.n_bands = desc->n_bands; ed.device = desc->device;
+        ed.n_channels = 2 * d.N_pad;
+        int rc = dspi_eq_create(&c->eq_m, &ed);
+        ed.n_channels = dspi::kOuts * d.N_pad;
+        if (rc == DSPI_OK) rc = dspi_eq_create(&c->eq_o, &ed);
+        if (rc != DSPI_OK) { dspi_chain_destroy(c); return rc; }
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = c->st.create();
 #define TRY(x) if (e == cudaSuccess) e = (x)
     TRY(dev_alloc(c, &c->d_aos, Np * dspi::kRoles * DSPI_MAX_BANDS));
-    TRY(dev_alloc(c, &d.coef, Np * dspi::kRoles * DSPI_MAX_BANDS * 8));
-    TRY(dev_alloc(c, &d.modes, Np * dspi::kRoles));
     TRY(dev_alloc(c, &d.preamp, 2 * Np));
     TRY(dev_alloc(c, &d.flags, Np));
     TRY(dev_alloc(c, &d.loud_c, 12 * Np));
@@ -768,8 +836,11 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     TRY(dev_alloc(c, &d.pdm, 9 * Np));
     TRY(dev_alloc(c, &d.peaks, dspi::kRoles * Np));
     TRY(dev_alloc(c, &d.clip, Np));
-    TRY(dev_alloc(c, &d.master, (size_t)2 * d.max_frames * Np, false));
-    TRY(dev_alloc(c, &d.subq, (size_t)d.max_frames * Np, false));
+    TRY(dev_alloc(c, &d.mrow, (size_t)2 * Np * d.ldF));
+    TRY(dev_alloc(c, &d.orow, (size_t)dspi::kOuts * Np * d.ldF));
+    TRY(dev_alloc(c, &d.subq, (size_t)Np * d.ldF));
+    TRY(dev_alloc(c, &d.skip_m, 2 * Np));
+    TRY(dev_alloc(c, &d.skip_o, dspi::kOuts * Np));
     TRY(dev_alloc(c, &c->d_status, Np));
     TRY(init_states(c));
 #undef TRY
@@ -799,7 +870,7 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
     const ChainDev &d = c->d;
     const size_t Np = d.N_pad;
     std::vector<float> preamp(2 * n), loud_c(12 * n), xf(7 * n), lev_c(9 * n), gl(9 * n), gr(9 * n), gain(9 * n);
-    std::vector<uint8_t> flags(n), loud_byp(n), oflags(9 * n);
+    std::vector<uint8_t> flags(n), loud_byp(n), oflags(9 * n), skip_m(2 * n), skip_o(9 * n);
     std::vector<int32_t> dly(9 * n);
     for (uint32_t i = 0; i < n; i++) {
         const dspi_chain_params_f32 &p = params[i];
@@ -825,6 +896,7 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
                 if (!oc.enabled && !p.matrix.outputs[partner].enabled) f |= dspi::O_PAIR_OFF;    // :930-933
             }
             oflags[o * n + i] = f;
+            skip_o[o * n + i] = (!oc.enabled || oc.mute) ? 1 : 0;            // :878-884: state frozen
             int32_t ds = oc.delay_samples;
             if (ds > DSPI_CHAIN_MAX_DELAY) ds = DSPI_CHAIN_MAX_DELAY;
             if (ds < 0) ds = 0;
@@ -835,6 +907,7 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
                    (p.crossfeed_enabled ? dspi::F_XFEED : 0) | (p.leveller_enabled ? dspi::F_LEV : 0) |
                    (p.leveller_lookahead ? dspi::F_LOOKAHEAD : 0) | (any_delay ? dspi::F_ANY_DELAY : 0) |
                    (p.matrix.outputs[dspi::kOuts - 1].enabled ? dspi::F_SUB_ON : 0);
+        skip_m[0 * n + i] = skip_m[1 * n + i] = p.bypass_master_eq ? 1 : 0;   // :721-728
         loud_byp[i] = (p.loudness[0].bypass ? 1 : 0) | (p.loudness[1].bypass ? 2 : 0);
         for (int j = 0; j < 2; j++) {
             const float v[6] = { p.loudness[j].sva1, p.loudness[j].sva2, p.loudness[j].sva3, p.loudness[j].svm0, p.loudness[j].svm1, p.loudness[j].svm2 };
@@ -861,8 +934,12 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
     CU_OK(put(d.o_gain, gain.data(), 9, 4));
     CU_OK(put(d.o_flags, oflags.data(), 9, 1));
     CU_OK(put(d.o_dly, dly.data(), 9, 4));
+    CU_OK(put(d.skip_m, skip_m.data(), 2, 1));
+    CU_OK(put(d.skip_o, skip_o.data(), 9, 1));
     CU_OK(cudaStreamSynchronize(c->stream));
-    return DSPI_OK;
+    int rc = dspi::eq_set_skip(c->eq_m, d.skip_m, c->stream);
+    if (rc == DSPI_OK) rc = dspi::eq_set_skip(c->eq_o, d.skip_o, c->stream);
+    return rc;
 }
 
 int dspi_chain_upload_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_biquad_f32 *biquads)
@@ -873,9 +950,16 @@ int dspi_chain_upload_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, const d
     CU_OK(cudaSetDevice(c->desc.device));
     const size_t row = (size_t)dspi::kRoles * DSPI_MAX_BANDS;
     CU_OK(cudaMemcpyAsync(c->d_aos + inst0 * row, biquads, n * row * sizeof(dspi_biquad_f32), cudaMemcpyHostToDevice, c->stream));
-    dspi::chain_pack_kernel<<<(n * dspi::kRoles + 127) / 128, 128, 0, c->stream>>>(c->d_aos, inst0, n, c->d);
+    const uint32_t Np = c->d.N_pad, items = n * dspi::kRoles * DSPI_MAX_BANDS;
+    dspi::chain_scatter_kernel<<<(items + 255) / 256, 256, 0, c->stream>>>(c->d_aos, inst0, n, Np, (dspi_biquad_f32 *)dspi::eq_aos_mirror(c->eq_m),
+                                                                          (dspi_biquad_f32 *)dspi::eq_aos_mirror(c->eq_o), 1);
     CU_OK(cudaGetLastError());
     c->launches++;
+    for (int role = 0; role < dspi::kRoles; role++) {
+        int rc = role < 2 ? dspi::eq_pack_range(c->eq_m, role * Np + inst0, n, c->stream)
+                          : dspi::eq_pack_range(c->eq_o, (role - 2) * Np + inst0, n, c->stream);
+        if (rc) return rc;
+    }
     CU_OK(cudaStreamSynchronize(c->stream));
     return DSPI_OK;
 }
@@ -886,7 +970,14 @@ int dspi_chain_download_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, dspi_
     if ((uint64_t)inst0 + n > c->desc.n_instances) return fail(DSPI_ERANGE, "instances [%u, %u) outside engine of %u", inst0, inst0 + n, c->desc.n_instances);
     if (n == 0) return DSPI_OK;
     CU_OK(cudaSetDevice(c->desc.device));
-    dspi::chain_unpack_kernel<<<(n * dspi::kRoles + 127) / 128, 128, 0, c->stream>>>(c->d_aos, inst0, n, c->d);
+    const uint32_t Np = c->d.N_pad, items = n * dspi::kRoles * DSPI_MAX_BANDS;
+    for (int role = 0; role < dspi::kRoles; role++) {
+        int rc = role < 2 ? dspi::eq_unpack_range(c->eq_m, role * Np + inst0, n, c->stream)
+                          : dspi::eq_unpack_range(c->eq_o, (role - 2) * Np + inst0, n, c->stream);
+        if (rc) return rc;
+    }
+    dspi::chain_scatter_kernel<<<(items + 255) / 256, 256, 0, c->stream>>>(c->d_aos, inst0, n, Np, (dspi_biquad_f32 *)dspi::eq_aos_mirror(c->eq_m),
+                                                                          (dspi_biquad_f32 *)dspi::eq_aos_mirror(c->eq_o), 0);
     CU_OK(cudaGetLastError());
     c->launches++;
     const size_t row = (size_t)dspi::kRoles * DSPI_MAX_BANDS;
@@ -946,6 +1037,9 @@ int dspi_chain_sync(dspi_chain *c)
 }
 
 void *dspi_chain_stream(dspi_chain *c) { return c ? (void *)c->stream : nullptr; }
-uint64_t dspi_chain_launch_count(dspi_chain *c) { return c ? c->launches : 0; }
+uint64_t dspi_chain_launch_count(dspi_chain *c)
+{
+    return c ? c->launches + dspi_eq_launch_count(c->eq_m) + dspi_eq_launch_count(c->eq_o) : 0;
+}
 
 }  // extern "C"

@@ -8,19 +8,20 @@
 namespace dspi {
 
 // state words (SoA, [9][Np]): err1 err2 x1 x2 y1 y2 err_acc rng fade_in_pos.
-// Modulates frames [f_begin, f_end) of instance `inst`: Q28 samples at subq[f * Np + inst],
-// 8 words (256 bits, MSB first) per frame to pdm_out[(inst * F + f) * 8 ..].
-__device__ __forceinline__ void pdm_modulate_frames(int32_t *__restrict__ pdm, const int32_t *__restrict__ subq, uint32_t Np, uint32_t inst,
-                                                    uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
+// Modulates frames [f_begin, f_end) of instance `inst`: Q28 samples at subq[f * frame_stride] (the
+// caller offsets `subq` to this instance), 8 words (256 bits, MSB first) per frame to
+// pdm_out[(inst * F + f) * 8 ..].
+__device__ __forceinline__ void pdm_modulate_frames(int32_t *__restrict__ pdm, const int32_t *__restrict__ subq, size_t frame_stride, uint32_t Np,
+                                                    uint32_t inst, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
     int32_t err1 = pdm[0 * Np + inst], err2 = pdm[1 * Np + inst];
     int32_t x1 = pdm[2 * Np + inst], x2 = pdm[3 * Np + inst], y1 = pdm[4 * Np + inst], y2 = pdm[5 * Np + inst];
     int32_t err_acc = pdm[6 * Np + inst];
     uint32_t rng = (uint32_t)pdm[7 * Np + inst], fade = (uint32_t)pdm[8 * Np + inst];
-    int32_t q_next = f_begin < f_end ? subq[(size_t)f_begin * Np + inst] : 0;
+    int32_t q_next = f_begin < f_end ? subq[(size_t)f_begin * frame_stride] : 0;
     for (uint32_t f = f_begin; f < f_end; f++) {
         int32_t pcm = q_next >> 14;                                          // :352
-        if (f + 1 < f_end) q_next = subq[(size_t)(f + 1) * Np + inst];       // next frame's load overlaps this frame's 256 decisions
+        if (f + 1 < f_end) q_next = subq[(size_t)(f + 1) * frame_stride];       // next frame's load overlaps this frame's 256 decisions
         pcm = max(-29500, min(29500, pcm));                                  // :353-354
         if (fade < 1024u) { pcm = (pcm * (int32_t)fade) >> 10; fade++; }     // :357-360
         const int32_t target = pcm + 32768;

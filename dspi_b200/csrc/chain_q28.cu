@@ -401,7 +401,7 @@ chainq_pdm_kernel(ChainQ d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32
     const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= d.N) return;
     if (!(d.flags[inst] & F_SUB_ON)) return;                                                              // usb_audio.c:1261
-    pdm_modulate_frames(d.pdm, d.subq, d.N_pad, inst, f_begin, f_end, F, pdm_out);
+    pdm_modulate_frames(d.pdm, d.subq + inst, d.N_pad, d.N_pad, inst, f_begin, f_end, F, pdm_out);
 }
 
 // filters[][] of n instances (instance-major AoS, 32-byte records) <-> [role][band][8][N_pad]

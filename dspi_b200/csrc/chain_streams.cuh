@@ -14,7 +14,7 @@ namespace dspi {
 struct ChainStreams {
     static constexpr int kMaxSlices = 8;
     cudaStream_t s_front = nullptr, s_out = nullptr, s_pdm = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_done = nullptr, ev_front[kMaxSlices] = {}, ev_out[kMaxSlices] = {};
+    cudaEvent_t ev_begin = nullptr, ev_done = nullptr, ev_aux = nullptr, ev_front[kMaxSlices] = {}, ev_out[kMaxSlices] = {};
 
     cudaError_t create()
     {
@@ -28,6 +28,7 @@ struct ChainStreams {
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_out, cudaStreamNonBlocking, lo);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_aux, cudaEventDisableTiming);
         for (int i = 0; i < kMaxSlices && e == cudaSuccess; i++) {
             e = cudaEventCreateWithFlags(&ev_front[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
@@ -39,7 +40,7 @@ struct ChainStreams {
     {
         for (cudaStream_t *s : { &s_front, &s_out, &s_pdm })
             if (*s) { cudaStreamSynchronize(*s); cudaStreamDestroy(*s); *s = nullptr; }
-        for (cudaEvent_t *ev : { &ev_begin, &ev_done })
+        for (cudaEvent_t *ev : { &ev_begin, &ev_done, &ev_aux })
             if (*ev) { cudaEventDestroy(*ev); *ev = nullptr; }
         for (int i = 0; i < kMaxSlices; i++) {
             if (ev_front[i]) { cudaEventDestroy(ev_front[i]); ev_front[i] = nullptr; }

@@ -69,7 +69,9 @@ struct dspi_eq {
     cudaStream_t stream, s_h2d, s_d2h;
     void *d_aos;             // Biquad[c_pad][12] in the reference layout (device mirror)
     void *d_coef;            // packed coefficient + state store
-    uint64_t *d_modes;       // float only
+    uint64_t *d_modes;       // float only: per-channel topology words as packed from the coefficient structs
+    uint64_t *d_modes_eff;   // with the caller's skip mask applied (chain engines), else nullptr
+    const uint8_t *d_skip;   // not owned
     uint32_t *d_sched;       // float only: dynamic scheduler words
     int n_sms;
     size_t aos_elem;
@@ -190,6 +192,7 @@ int dspi_eq_destroy(dspi_eq *e)
     if (e->d_aos) cudaFree(e->d_aos);
     if (e->d_coef) cudaFree(e->d_coef);
     if (e->d_modes) cudaFree(e->d_modes);
+    if (e->d_modes_eff) cudaFree(e->d_modes_eff);
     if (e->d_sched) cudaFree(e->d_sched);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
@@ -284,7 +287,7 @@ static int refresh_kernel_choice(dspi_eq *e)
     const uint32_t step = C > 2048 ? C / 2048 : 1;
     const uint32_t cnt = (C + step - 1) / step;
     std::vector<uint64_t> w(cnt);
-    CU_OK(cudaMemcpy2DAsync(w.data(), 8, e->d_modes, (size_t)step * 8, 8, cnt, cudaMemcpyDeviceToHost, e->stream));
+    CU_OK(cudaMemcpy2DAsync(w.data(), 8, e->d_modes_eff ? e->d_modes_eff : e->d_modes, (size_t)step * 8, 8, cnt, cudaMemcpyDeviceToHost, e->stream));
     CU_OK(cudaStreamSynchronize(e->stream));
     const uint64_t mask = (1ull << (4 * nb)) - 1;                // nb <= 12
     for (auto &x : w) x &= mask;
@@ -343,7 +346,8 @@ static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint3
     a.ld = ld;
     a.coef = q28 ? (void *)((int32_t *)e->d_coef + (size_t)g0 * DSPI_MAX_BANDS * 20 * 32)
                  : (void *)((float *)e->d_coef + (size_t)g0 * DSPI_MAX_BANDS * 8 * 32 * e->cpl);
-    a.modes = e->d_modes ? e->d_modes + (size_t)g0 * e->rows : nullptr;
+    const uint64_t *modes = e->d_modes_eff ? e->d_modes_eff : e->d_modes;
+    a.modes = modes ? modes + (size_t)g0 * e->rows : nullptr;
     a.n_groups = ng;
     a.sched = e->d_sched;
     a.n_sms = e->n_sms;
@@ -367,6 +371,74 @@ static int launch_eq(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, uint3
     e->launches++;
     return DSPI_OK;
 }
+
+}  // extern "C"
+
+// ---- engine-internal interface (eq_kernels.cuh) ------------------------------------------------
+namespace dspi {
+
+void *eq_aos_mirror(dspi_eq *e) { return e->d_aos; }
+
+static int remask(dspi_eq *e, cudaStream_t s)
+{
+    if (!e->d_skip || !e->d_modes) return DSPI_OK;
+    if (!e->d_modes_eff) {
+        CU_OK(cudaMalloc(&e->d_modes_eff, (size_t)e->c_pad * 8));
+        CU_OK(cudaMemsetAsync(e->d_modes_eff, 0, (size_t)e->c_pad * 8, s));
+    }
+    CU_OK(launch_mask_modes(e->d_modes, e->d_skip, e->d_modes_eff, e->desc.n_channels, s));
+    e->launches++;
+    e->sig_dirty = true;
+    return DSPI_OK;
+}
+
+int eq_pack_range(dspi_eq *e, uint32_t ch0, uint32_t n, cudaStream_t s)
+{
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(e->desc.device));
+    if (e->desc.arith == DSPI_ARITH_Q28)
+        CU_OK(launch_pack_q28((const dspi_biquad_q28 *)e->d_aos, ch0, n, (int32_t *)e->d_coef, s));
+    else
+        CU_OK(launch_pack_f32((const dspi_biquad_f32 *)e->d_aos, ch0, n, (float *)e->d_coef, e->d_modes, e->cpl, s));
+    e->launches++;
+    e->sig_dirty = true;
+    int rc = remask(e, s);
+    if (rc) return rc;
+    CU_OK(cudaStreamSynchronize(s));
+    return DSPI_OK;
+}
+
+int eq_unpack_range(dspi_eq *e, uint32_t ch0, uint32_t n, cudaStream_t s)
+{
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(e->desc.device));
+    if (e->desc.arith == DSPI_ARITH_Q28)
+        CU_OK(launch_unpack_q28((dspi_biquad_q28 *)e->d_aos, ch0, n, (const int32_t *)e->d_coef, s));
+    else
+        CU_OK(launch_unpack_f32((dspi_biquad_f32 *)e->d_aos, ch0, n, (const float *)e->d_coef, e->cpl, s));
+    e->launches++;
+    return DSPI_OK;
+}
+
+int eq_set_skip(dspi_eq *e, const uint8_t *d_skip, cudaStream_t s)
+{
+    CU_OK(cudaSetDevice(e->desc.device));
+    e->d_skip = d_skip;
+    int rc = remask(e, s);
+    if (rc) return rc;
+    CU_OK(cudaStreamSynchronize(s));
+    return DSPI_OK;
+}
+
+int eq_process_on(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStream_t s)
+{
+    if (T == 0) return DSPI_OK;
+    return launch_eq(e, d_samples, T, ld, 0, e->n_groups, e->desc.n_channels, s);
+}
+
+}  // namespace dspi
+
+extern "C" {
 
 int dspi_eq_kernel_info(dspi_eq *e, char *buf, size_t cap)
 {

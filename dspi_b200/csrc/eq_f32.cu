@@ -152,6 +152,17 @@ cudaError_t launch_pack_f32(const dspi_biquad_f32 *aos, uint32_t ch0, uint32_t n
     pack_f32_kernel<<<(n + 127) / 128, 128, 0, stream>>>(aos, ch0, n, coef, modes, cpl);
     return cudaGetLastError();
 }
+__global__ void mask_modes_kernel(const uint64_t *__restrict__ raw, const uint8_t *__restrict__ skip, uint64_t *__restrict__ eff, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) eff[i] = skip[i] ? 0ull : raw[i];
+}
+cudaError_t launch_mask_modes(const uint64_t *raw, const uint8_t *skip, uint64_t *eff, uint32_t n, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    mask_modes_kernel<<<(n + 255) / 256, 256, 0, stream>>>(raw, skip, eff, n);
+    return cudaGetLastError();
+}
 cudaError_t launch_unpack_f32(dspi_biquad_f32 *aos, uint32_t ch0, uint32_t n, const float *coef, int cpl, cudaStream_t stream)
 {
     if (n == 0) return cudaSuccess;

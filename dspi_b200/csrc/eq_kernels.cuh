@@ -37,3 +37,18 @@ cudaError_t launch_pack_q28(const dspi_biquad_q28 *aos, uint32_t ch0, uint32_t n
 cudaError_t launch_unpack_q28(dspi_biquad_q28 *aos, uint32_t ch0, uint32_t n, const int32_t *coef, cudaStream_t stream);
 
 }  // namespace dspi
+
+// ---- engine-internal interface (engine.cu), used by the chain engines which run their EQ rows
+// through K1: same packed store, same kernels, on a stream of the caller's choosing -------------
+struct dspi_eq;
+namespace dspi {
+void *eq_aos_mirror(dspi_eq *e);                                          // device Biquad[c_pad][12], reference layout
+int eq_pack_range(dspi_eq *e, uint32_t ch0, uint32_t n, cudaStream_t s);   // mirror -> packed store (coefficients and state), synchronous
+int eq_unpack_range(dspi_eq *e, uint32_t ch0, uint32_t n, cudaStream_t s); // packed store -> mirror (state), asynchronous on s
+// rows with skip[ch] != 0 keep their whole cascade frozen (all bands treated as bypassed, state untouched):
+// usb_audio.c:721-728 (bypass_master_eq), :879-884 (muted / disabled outputs).  `d_skip` is [n_channels]
+// device memory owned by the caller; call again after changing it.
+int eq_set_skip(dspi_eq *e, const uint8_t *d_skip, cudaStream_t s);
+int eq_process_on(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStream_t s);
+cudaError_t launch_mask_modes(const uint64_t *raw, const uint8_t *skip, uint64_t *eff, uint32_t n, cudaStream_t stream);
+}  // namespace dspi
