@@ -86,6 +86,45 @@ __device__ __forceinline__ uint32_t chunk(int32_t &err1, int32_t &err2, int32_t 
     return word;
 }
 
+// U chunks of 32 decisions unrolled per loop iteration: straight-line code size vs the instruction caches
+// (chain_pdm.cuh unrolls a whole 256-bit frame = 8 chunks)
+template <int U>
+__global__ void ku(int32_t *st, uint32_t *out, long long *cyc, int iters)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t err1 = st[tid * 2], err2 = st[tid * 2 + 1];
+    const int32_t target = 32768 + (tid * 37 % 20000) - 10000;
+    uint32_t h = 0;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < iters; it += U) {
+#pragma unroll
+        for (int c = 0; c < U; c++) {
+            const int32_t dither = (int32_t)((h >> 7) & 255) - 128;
+            h = h * 1664525u + chunk<5>(err1, err2, target, dither);
+        }
+        err1 -= err1 >> 16; err2 -= err2 >> 16;
+    }
+    const long long t1 = clock64();
+    out[tid] = h ^ (uint32_t)err1 ^ (uint32_t)err2;
+    if (threadIdx.x % 32 == 0) cyc[tid / 32] = t1 - t0;
+}
+
+template <int U>
+void run_u(int32_t *st, uint32_t *out, long long *cyc)
+{
+    const int iters = 4096, nsm = 148, w = 4;
+    ku<U><<<nsm, 32 * w>>>(st, out, cyc, iters);
+    cudaDeviceSynchronize();
+    ku<U><<<nsm, 32 * w>>>(st, out, cyc, iters);
+    cudaDeviceSynchronize();
+    static long long h_cyc[148 * 16];
+    cudaMemcpy(h_cyc, cyc, sizeof(long long) * nsm * w, cudaMemcpyDeviceToHost);
+    long long mx = 0;
+    for (int i = 0; i < nsm * w; i++) mx = h_cyc[i] > mx ? h_cyc[i] : mx;
+    printf("imad two-sum, %d chunks unrolled per iteration: cycles/bit %.2f (%s)\n", U, (double)mx / (iters * 32.0), cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int V>
 __global__ void k(int32_t *st, uint32_t *out, long long *cyc, int iters)
 {
@@ -128,6 +167,7 @@ int main()
     int32_t *st; uint32_t *out; long long *cyc;
     cudaMalloc(&st, 148 * 512 * 8); cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 148 * 16 * 8);
     cudaMemset(st, 0, 148 * 512 * 8);
+    run_u<1>(st, out, cyc); run_u<2>(st, out, cyc); run_u<4>(st, out, cyc); run_u<8>(st, out, cyc); run_u<16>(st, out, cyc);
     for (int w : {4, 8, 16}) {
         run<0>("reference shape", st, out, cyc, w);
         run<1>("mask form (old)", st, out, cyc, w);
