@@ -225,6 +225,29 @@ def extra_configs(api, W, L, torch):
         engq.close()
         out["cfg3_q28_chain_8192inst"] = {"instance_frames_per_s": N * F / (msq * 1e-3), "output_channel_samples_per_s": N * 5 * F / (msq * 1e-3),
                                           "ms_per_step": msq, "instances": N, "frames": F, "realtime_factor": (F / FS) / (msq * 1e-3), "timing": "host clock around synchronised calls"}
+        # S/PDIF subframe encoder (the step after the chain): 32768 stereo streams x 6144 frames, 24 B per frame
+        ns, Fs = 4 * N, 6144
+        nrot = 3                                                            # rotate buffers: 1.6 GB + 3.2 GB each, larger than L2
+        wbuf = [torch.randint(-2**23, 2**23, (ns, Fs, 2), dtype=torch.int32, device="cuda") for _ in range(nrot)]
+        obuf = [torch.empty((ns, Fs, 2, 2), dtype=torch.int32, device="cuda") for _ in range(nrot)]
+        torch.cuda.synchronize()
+        cur = torch.cuda.current_stream()
+        for i in range(3):
+            api.spdif_encode_device(wbuf[i % nrot].data_ptr(), ns, Fs, obuf[i % nrot].data_ptr(), stream=cur.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 9
+        e0.record(cur)
+        for i in range(reps):
+            api.spdif_encode_device(wbuf[i % nrot].data_ptr(), ns, Fs, obuf[i % nrot].data_ptr(), stream=cur.cuda_stream)
+        e1.record(cur)
+        torch.cuda.synchronize()
+        mss = e0.elapsed_time(e1) / reps
+        peak, _ = measured_peak_gbs()
+        gbs = ns * Fs * 24 / (mss * 1e-3) / 1e9
+        out["spdif_encode_32768streams"] = {"frames_per_s": ns * Fs / (mss * 1e-3), "ms_per_step": mss, "streams": ns, "frames": Fs,
+                                            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                                         "kernel": "spdif_encode_kernel", "algorithmic_bytes_per_launch": ns * Fs * 24}}
+        del wbuf, obuf
     except Exception as e:                     # extras must never break the headline line
         out["error"] = repr(e)
     return out

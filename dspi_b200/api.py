@@ -30,6 +30,7 @@ SYMBOLS = [
     "dspi_chainq_create", "dspi_chainq_destroy", "dspi_chainq_set_params", "dspi_chainq_upload_biquads", "dspi_chainq_download_biquads",
     "dspi_chainq_reset_state", "dspi_chainq_process_host", "dspi_chainq_process_device", "dspi_chainq_sync", "dspi_chainq_launch_count",
     "dspi_crossfeed_compute_coefficients_q28", "dspi_loudness_compute_table_q28",
+    "dspi_spdif_lookup_table", "dspi_spdif_encode_device", "dspi_spdif_encode_host",
 ]
 
 
@@ -328,6 +329,34 @@ def loudness_table(fs, ref_spl=83.0, intensity_pct=100.0):
     t = np.zeros((L.LOUD_STEPS, 2), L.LOUD_F32)
     lib().dspi_loudness_compute_table_f32(t.ctypes.data, ref_spl, intensity_pct, fs)
     return t
+
+
+SPDIF_CHANNEL_STATUS = bytes([0x04, 0x00, 0x00, 0x00, 0x0B])       # audio_spdif.c:82-88 (byte 3 = sample-rate code, set at run time)
+
+
+def spdif_lookup_table():
+    """The reference's 256-entry biphase-mark table (``audio_spdif.c:141-153``)."""
+    t = np.zeros(256, np.uint32)
+    lib().dspi_spdif_lookup_table(t.ctypes.data_as(C.c_void_p))
+    return t
+
+
+def spdif_encode_device(d_words, n_streams, frames, d_subframes, block_pos0=0, channel_status=SPDIF_CHANNEL_STATUS, device=0, stream=None):
+    """Device pointers in/out: ``[n_streams][frames][2]`` int32 words -> ``[n_streams][frames][2][2]`` uint32 {l, h}."""
+    cs = (C.c_uint8 * 5)(*channel_status)
+    _check(lib().dspi_spdif_encode_device(int(device), C.c_void_p(int(d_words)), C.c_uint64(int(n_streams)), int(frames), int(block_pos0), cs,
+                                          C.c_void_p(int(d_subframes)), C.c_void_p(int(stream) if stream else None)))
+
+
+def spdif_encode_host(words, block_pos0=0, channel_status=SPDIF_CHANNEL_STATUS, device=0):
+    """``words`` int32 ``[n_streams, frames, 2]`` (host) -> uint32 ``[n_streams, frames, 2, 2]`` ({l, h} per subframe)."""
+    w = np.ascontiguousarray(words, np.int32)
+    assert w.ndim == 3 and w.shape[2] == 2
+    out = np.empty(w.shape + (2,), np.uint32)
+    cs = (C.c_uint8 * 5)(*channel_status)
+    _check(lib().dspi_spdif_encode_host(int(device), w.ctypes.data_as(C.c_void_p), C.c_uint64(w.shape[0]), int(w.shape[1]), int(block_pos0), cs,
+                                        out.ctypes.data_as(C.c_void_p)))
+    return out
 
 
 def host_volume(volume_8_8):

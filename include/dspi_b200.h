@@ -318,6 +318,25 @@ uint64_t dspi_chainq_launch_count(dspi_chainq *c);
 void dspi_crossfeed_compute_coefficients_q28(dspi_crossfeed_state_q28 *st, const dspi_crossfeed_config *cfg, float sample_rate);
 void dspi_loudness_compute_table_q28(dspi_loudness_coeffs_q28 table[61][2], float ref_spl, float intensity_pct, float sample_rate);
 
+/* ---- S/PDIF (IEC 60958) subframe encoder: the step after the chain -------------------------- */
+/* What stereo_to_spdif_producer_give_s32() does with every S/PDIF producer buffer
+ * (pico_audio_spdif_multi/sample_encoding.cpp:42-50 -> spdif_update_subframe,
+ * include/pico/audio_spdif/sample_encoding.h:27-50), together with the preamble / channel-status /
+ * validity-user-status-parity stamping of init_spdif_buffer (audio_spdif.c:99-114) and the
+ * block-position fix-up at DMA start (:372-388): 24-bit words in, 64-bit biphase-mark subframes out,
+ * ready for the 2-bits-per-cell PIO serialiser. */
+typedef struct { uint32_t l, h; } dspi_spdif_subframe;           /* spdif_subframe_t, sample_encoding.h:20-23 */
+/* the reference's 256-entry table (audio_spdif.c:141-153), for hosts that keep its table-driven encoder */
+void dspi_spdif_lookup_table(uint32_t table[256]);
+/* words: [n_streams][frames][2] int32 (bits 23:0 used) - the layout dspi_chain_process_* writes with
+ * n_streams = 4 * n_instances; subframes: [n_streams][frames][2] {l, h}.  Frame n of every stream sits at
+ * block position (block_pos0 + n) % 192; channel_status = the 5 consumer status bytes (audio_spdif.c:82-88).
+ * _device is asynchronous on `cuda_stream` (a cudaStream_t, may be NULL); _host copies in and out. */
+int dspi_spdif_encode_device(int device, const int32_t *d_words, uint64_t n_streams, uint32_t frames, uint32_t block_pos0,
+                             const uint8_t channel_status[5], dspi_spdif_subframe *d_subframes, void *cuda_stream);
+int dspi_spdif_encode_host(int device, const int32_t *words, uint64_t n_streams, uint32_t frames, uint32_t block_pos0,
+                           const uint8_t channel_status[5], dspi_spdif_subframe *subframes);
+
 /* pinned host memory helpers */
 void *dspi_host_alloc(size_t bytes);
 void dspi_host_free(void *p);

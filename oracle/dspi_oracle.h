@@ -248,6 +248,11 @@ void orc_q28_xfeed(orc_xfeed_q28 *st, int32_t *l, int32_t *r, uint32_t count); /
 void orc_f32s_leveller(orc_lev_state_f32 *st, const orc_lev_coeffs *c, int lookahead, float *l, float *r, uint32_t count);  /* leveller.c:148-262 */
 void orc_f32f_leveller(orc_lev_state_f32 *st, const orc_lev_coeffs *c, int lookahead, float *l, float *r, uint32_t count);
 void orc_q28_leveller(orc_lev_state_q28 *st, const orc_lev_coeffs *c, int lookahead, int32_t *l, int32_t *r, uint32_t count); /* leveller.c:275-389 */
+/* ---- S/PDIF subframe encoder (orc_spdif.c; pico_audio_spdif_multi) ---- */
+void orc_spdif_lookup_init(uint32_t table[256]);                                                  /* audio_spdif.c:141-153 */
+void orc_spdif_update_subframe(const uint32_t table[256], uint32_t *l, uint32_t *h, int32_t sample);  /* sample_encoding.h:27-50 */
+void orc_spdif_encode(const uint32_t table[256], const int32_t *words, uint32_t frames, uint32_t pos0, const uint8_t cs[5], uint32_t *out);
+
 void orc_pdm_reset(orc_pdm_state *st);
 void orc_pdm_modulate(orc_pdm_state *st, int32_t sample_q28, uint32_t out[8]);  /* pdm_generator.c:351-397 */
 

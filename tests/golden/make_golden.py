@@ -9,7 +9,10 @@ Fixture A  "cfg1": BASELINE config 1 - 2 channels x 3 bands @48 kHz (SURVEY.md Â
            10 kHz +2 dB Q.707 (TDF2), bands 3-9 flat; inputs: impulse, 1 kHz sine -6 dBFS,
            log sweep 20 Hz-20 kHz, xorshift32 s16 noise; 100 packets x 48 samples.
 Fixture B  "mix":  24 channels, random per-band types (all six), 96 kHz, 960 samples.
-Each holds coefficients (reference dsp_compute_coefficients), inputs, and outputs + final
+Fixture C  "spdif": 3 stereo streams x 421 frames of 24-bit words (edge values + random) through the
+           reference's own spdif_update_subframe (compiled from its header, oracle/ref_spdif_shim.c) over
+           buffers stamped as init_spdif_buffer does, block position starting at 187.
+Each of A and B holds coefficients (reference dsp_compute_coefficients), inputs, and outputs + final
 filter state of dsp_process_channel_block for the strict, fused and Q28 builds.
 """
 import os
@@ -21,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from dspi_b200 import layouts as L          # noqa: E402
 from dspi_b200 import workloads as W        # noqa: E402
-from tests.orc import Ref, build_oracle     # noqa: E402
+from tests.orc import Ref, RefSpdif, Oracle, build_oracle     # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -95,7 +98,23 @@ def main():
     np.savez_compressed(os.path.join(HERE, "mix.npz"), params=params, x=x, bq_f32=r["f32s"][0], bq_q28=r["q28"][0],
                         f32s_y=r["f32s"][1], f32s_state=r["f32s"][2], f32f_y=r["f32f"][1], f32f_state=r["f32f"][2],
                         q28_x=r["q28"][3], q28_y=r["q28"][1], q28_state=r["q28"][2])
-    for f in ("cfg1.npz", "mix.npz"):
+    # ---- fixture C: S/PDIF subframes
+    cs = bytes([0x04, 0x00, 0x00, 0x02, 0x0B])
+    rng = np.random.default_rng(60958)
+    n_streams, frames, pos0 = 3, 421, 187
+    words = rng.integers(-2**31, 2**31, (n_streams, frames, 2), dtype=np.int64).astype(np.int32)
+    words[0, :10, 0] = [0, 1, -1, 0x7FFFFF, -0x800000, 0x800000, 0xFFFFFF, 0x1000000, 0x55AA55, -0x55AA56]
+    rs = RefSpdif(Oracle().spdif_table())                        # the table itself is restated (audio_spdif.c:141-153)
+    sub = np.zeros((n_streams, frames, 2, 2), np.uint32)
+    for s_ in range(n_streams):
+        for n in range(frames):
+            pos = (pos0 + n) % 192
+            c = (cs[pos // 8] >> (pos % 8)) & 1 if pos < 40 else 0
+            sub[s_, n, 0] = (0x39 if pos == 0 else 0xC9, 0x55000000 | (c << 29))
+            sub[s_, n, 1] = (0x69, 0x55000000 | (c << 29))
+        rs.copy_s32(sub[s_], words[s_])
+    np.savez_compressed(os.path.join(HERE, "spdif.npz"), words=words, subframes=sub, pos0=np.uint32(pos0), cs=np.frombuffer(cs, np.uint8))
+    for f in ("cfg1.npz", "mix.npz", "spdif.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

@@ -59,6 +59,9 @@ class Oracle:
             f = getattr(L, f"orc_{fl}_chain_packet")
             f.restype = _u32
             f.argtypes = [_vp, _vp, _u32, _u32, _vp, _u32, _vp]
+        L.orc_spdif_lookup_init.argtypes = [_vp]
+        L.orc_spdif_update_subframe.argtypes = [_vp, _vp, _vp, C.c_int32]
+        L.orc_spdif_encode.argtypes = [_vp, _vp, _u32, _u32, _vp, _vp]
         L.orc_eq_coeffs_f32.argtypes = [_vp, _vp, C.c_float]
         L.orc_eq_coeffs_q28.argtypes = [_vp, _vp, C.c_float]
         L.orc_xfeed_coeffs_f32.argtypes = [_vp, _vp, C.c_float]
@@ -100,6 +103,26 @@ class Oracle:
         return out
 
     # -- parameters ----------------------------------------------------------
+    def spdif_table(self):
+        t = np.zeros(256, np.uint32)
+        self.lib.orc_spdif_lookup_init(t.ctypes.data)
+        return t
+
+    def spdif_update(self, table, l, h, sample):
+        a, b = C.c_uint32(l), C.c_uint32(h)
+        self.lib.orc_spdif_update_subframe(table.ctypes.data, C.addressof(a), C.addressof(b), int(np.int32(sample)))
+        return int(a.value), int(b.value)
+
+    def spdif_encode(self, words, pos0=0, cs=bytes([0x04, 0, 0, 0, 0x0B])):
+        """``words`` int32 [n_streams, frames, 2] -> uint32 [n_streams, frames, 2, 2]; every stream starts at pos0."""
+        w = np.ascontiguousarray(words, np.int32)
+        out = np.empty(w.shape + (2,), np.uint32)
+        table = self.spdif_table()
+        csb = np.frombuffer(bytes(cs), np.uint8).copy()
+        for s_ in range(w.shape[0]):
+            self.lib.orc_spdif_encode(table.ctypes.data, w[s_].ctypes.data, int(w.shape[1]), int(pos0), csb.ctypes.data, out[s_].ctypes.data)
+        return out
+
     def eq_coeffs(self, q28, params, bq, fs):
         """params: EQ_PARAM[N] (mutated: clamps written back); bq: matching biquads."""
         fn = self.lib.orc_eq_coeffs_q28 if q28 else self.lib.orc_eq_coeffs_f32
@@ -109,6 +132,33 @@ class Oracle:
         sp, sb = pp.dtype.itemsize, bb.dtype.itemsize
         for i in range(pp.shape[0]):
             fn(base_p + i * sp, base_b + i * sb, fs)
+
+
+class RefSpdif:
+    """The reference's own ``spdif_update_subframe`` compiled from its header (oracle/ref_spdif_shim.c)."""
+
+    PATH = os.path.join(ORACLE_DIR, "_ref", "libdspi_ref_spdif.so")
+
+    @staticmethod
+    def available():
+        return os.path.exists(RefSpdif.PATH)
+
+    def __init__(self, table):
+        self.lib = L = C.CDLL(RefSpdif.PATH)
+        L.ref_spdif_set_lookup.argtypes = [_vp]
+        L.ref_spdif_update_subframe.argtypes = [_vp, C.c_int32]
+        L.ref_spdif_copy_s32.argtypes = [_vp, _vp, _u32]
+        t = np.ascontiguousarray(table, np.uint32)
+        L.ref_spdif_set_lookup(t.ctypes.data)
+
+    def update(self, l, h, sample):
+        lh = np.array([l, h], np.uint32)
+        self.lib.ref_spdif_update_subframe(lh.ctypes.data, int(np.int32(sample)))
+        return int(lh[0]), int(lh[1])
+
+    def copy_s32(self, subframes, words):
+        """In place: ``subframes`` uint32 [n, 2, 2] updated with ``words`` int32 [n, 2]."""
+        self.lib.ref_spdif_copy_s32(subframes.ctypes.data, words.ctypes.data, int(words.shape[0]))
 
 
 class Ref:

@@ -31,6 +31,12 @@ def test_mix(oracle, flavour):
     assert same_bits(bq, g[f"{flavour}_state"])
 
 
+def test_spdif_fixture(oracle):
+    g = load_golden("spdif.npz")
+    got = oracle.spdif_encode(g["words"], int(g["pos0"]), bytes(g["cs"]))
+    assert np.array_equal(got, g["subframes"])
+
+
 def test_cfg1_known_answers():
     """KATs the reference states in comments: flat band => bypass with b0 = 1; path split at fs/7.5."""
     g = load_golden("cfg1.npz")
