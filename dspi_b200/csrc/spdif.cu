@@ -57,14 +57,18 @@ __device__ __forceinline__ uint2 encode_subframe(int32_t sample, uint32_t pre, u
 }
 
 __global__ void __launch_bounds__(256)
-spdif_encode_kernel(const int2 *__restrict__ words, uint4 *__restrict__ out, uint64_t total, uint32_t frames, uint32_t pos0, uint64_t cs40)
+spdif_encode_kernel(const int2 *__restrict__ words, uint4 *__restrict__ out, uint64_t n_streams, uint32_t frames, uint32_t pos0, uint64_t cs40)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t n = (uint32_t)(i % frames);
-        const uint32_t pos = (pos0 + n) % 192u;
-        const uint32_t c = pos < 40u ? (uint32_t)(cs40 >> pos) & 1u : 0u;      // audio_spdif.c:91-94
+    // grid.x walks the frames of a stream, grid.y the streams: no 64-bit division anywhere
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= frames) return;
+    const uint32_t pos = (pos0 + n) % 192u;
+    const uint32_t c = pos < 40u ? (uint32_t)(cs40 >> pos) & 1u : 0u;          // audio_spdif.c:91-94
+    const uint32_t pre_l = pos == 0 ? 0x39u : 0xC9u;                          // Z at block start, X elsewhere (:77-79, :104, :374)
+    for (uint64_t s = blockIdx.y; s < n_streams; s += gridDim.y) {
+        const uint64_t i = s * frames + n;
         const int2 w = words[i];
-        const uint2 a = encode_subframe(w.x, pos == 0 ? 0x39u : 0xC9u, c);    // Z at block start, X elsewhere (:77-79, :104, :374)
+        const uint2 a = encode_subframe(w.x, pre_l, c);
         const uint2 b = encode_subframe(w.y, 0x69u, c);                        // Y
         out[i] = make_uint4(a.x, a.y, b.x, b.y);
     }
@@ -116,14 +120,16 @@ int dspi_spdif_encode_device(int device, const int32_t *d_words, uint64_t n_stre
     CU_OK(cudaSetDevice(device));
     uint64_t cs40 = 0;
     for (int i = 0; i < 5; i++) cs40 |= (uint64_t)channel_status[i] << (8 * i);
-    const uint64_t total = n_streams * frames;
     int n_sms = 148;
     cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
-    uint64_t blocks = (total + 255) / 256;
-    const uint64_t cap = (uint64_t)n_sms * 8 * 4;                            // 8 resident CTAs per SM, 4 waves
-    if (blocks > cap) blocks = cap;
-    dspi::spdif_encode_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>((const int2 *)d_words, (uint4 *)d_subframes, total, frames,
-                                                                                      block_pos0 % 192u, cs40);
+    const uint32_t bx = (frames + 255) / 256;
+    // enough CTAs for ~4 waves of 8 resident CTAs per SM; every CTA then loops over streams
+    uint64_t by = ((uint64_t)n_sms * 8 * 4 + bx - 1) / bx;
+    if (by > n_streams) by = n_streams;
+    if (by > 65535) by = 65535;
+    if (by == 0) by = 1;
+    dspi::spdif_encode_kernel<<<dim3(bx, (unsigned)by), 256, 0, (cudaStream_t)cuda_stream>>>((const int2 *)d_words, (uint4 *)d_subframes, n_streams, frames,
+                                                                                            block_pos0 % 192u, cs40);
     CU_OK(cudaGetLastError());
     return DSPI_OK;
 }
