@@ -31,6 +31,7 @@ SYMBOLS = [
     "dspi_chainq_reset_state", "dspi_chainq_process_host", "dspi_chainq_process_device", "dspi_chainq_sync", "dspi_chainq_launch_count",
     "dspi_crossfeed_compute_coefficients_q28", "dspi_loudness_compute_table_q28",
     "dspi_spdif_lookup_table", "dspi_spdif_encode_device", "dspi_spdif_encode_host",
+    "dspi_bulk_state_defaults", "dspi_bulk_params_apply", "dspi_bulk_params_collect", "dspi_bulk_state_to_chain_f32", "dspi_bulk_state_to_chain_q28",
 ]
 
 
@@ -329,6 +330,39 @@ def loudness_table(fs, ref_spl=83.0, intensity_pct=100.0):
     t = np.zeros((L.LOUD_STEPS, 2), L.LOUD_F32)
     lib().dspi_loudness_compute_table_f32(t.ctypes.data, ref_spl, intensity_pct, fs)
     return t
+
+
+def bulk_state_defaults(platform=L.PLATFORM_RP2350):
+    """Power-on values of the globals ``bulk_params_apply`` edits (one ``BULK_STATE`` record)."""
+    st = np.zeros(1, L.BULK_STATE)
+    lib().dspi_bulk_state_defaults(st.ctypes.data_as(C.c_void_p), int(platform))
+    return st
+
+
+def bulk_params_apply(wire, state, exact_db=False):
+    """``bulk_params_apply`` (bulk_params.c:178-377) on ``state`` (in place).  Returns the firmware's code: 0, -1 .. -4."""
+    w = np.ascontiguousarray(wire).view(np.uint8).reshape(-1)
+    assert w.size == L.WIRE_BULK.itemsize and state.dtype == L.BULK_STATE
+    return int(lib().dspi_bulk_params_apply(w.ctypes.data_as(C.c_void_p), state.ctypes.data_as(C.c_void_p), int(bool(exact_db))))
+
+
+def bulk_params_collect(state):
+    """``bulk_params_collect`` (bulk_params.c:62-172): one ``WIRE_BULK`` record."""
+    out = np.zeros(1, L.WIRE_BULK)
+    lib().dspi_bulk_params_collect(state.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def bulk_state_to_chain(state, fs, host_volume_8_8=0, host_mute=False, biquads=None):
+    """What the main loop derives after an apply: (chain params [1], biquads [1, roles, 12]) for the state's platform."""
+    q28 = int(state["platform"][0]) == L.PLATFORM_RP2040
+    P = np.zeros(1, L.CHAIN_PARAMS_Q28 if q28 else L.CHAIN_PARAMS_F32)
+    roles = L.CHAINQ_EQ_CHANNELS if q28 else L.CHAIN_EQ_CHANNELS
+    bq = np.zeros((1, roles, L.MAX_BANDS), L.BIQUAD_Q28 if q28 else L.BIQUAD_F32) if biquads is None else biquads
+    fn = lib().dspi_bulk_state_to_chain_q28 if q28 else lib().dspi_bulk_state_to_chain_f32
+    _check(fn(state.ctypes.data_as(C.c_void_p), C.c_float(fs), C.c_int16(int(host_volume_8_8)), int(bool(host_mute)),
+              P.ctypes.data_as(C.c_void_p), bq.ctypes.data_as(C.c_void_p)))
+    return P, bq
 
 
 SPDIF_CHANNEL_STATUS = bytes([0x04, 0x00, 0x00, 0x00, 0x0B])       # audio_spdif.c:82-88 (byte 3 = sample-rate code, set at run time)

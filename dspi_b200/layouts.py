@@ -117,3 +117,41 @@ CHAIN_PARAMS_Q28 = np.dtype({
     "offsets": [0, 1, 2, 3, 4, 5, 8, 12, 16, 20, 28, 76, 104, 140],
     "itemsize": 360})
 assert MATRIX_MIXER_Q28.itemsize == 220 and STATUS_Q28.itemsize == 18 and CHAIN_PARAMS_Q28.itemsize == 360
+
+# ---- bulk parameter packet (bulk_params.h:40-205) and the device state it edits -----------------
+WIRE_MAX_CHANNELS, WIRE_MAX_OUTPUTS = 11, 9
+PLATFORM_RP2040, PLATFORM_RP2350 = 0, 1
+WIRE_BULK = np.dtype([
+    ("header", [("format_version", _b), ("platform_id", _b), ("num_channels", _b), ("num_output_channels", _b), ("num_input_channels", _b),
+                ("max_bands", _b), ("payload_length", np.uint16), ("fw_version_major", np.uint16), ("fw_version_minor", np.uint16), ("reserved", _u)]),
+    ("global", [("preamp_gain_db", _f), ("bypass", _b), ("loudness_enabled", _b), ("reserved", _b, (2,)), ("loudness_ref_spl", _f),
+                ("loudness_intensity_pct", _f)]),
+    ("crossfeed", [("enabled", _b), ("preset", _b), ("itd_enabled", _b), ("reserved", _b), ("custom_fc", _f), ("custom_feed_db", _f), ("reserved2", _u)]),
+    ("legacy", [("gain_db", _f, (3,)), ("mute", _b, (3,)), ("reserved", _b)]),
+    ("delays", [("delay_ms", _f, (WIRE_MAX_CHANNELS,))]),
+    ("crosspoints", [("enabled", _b), ("phase_invert", _b), ("reserved", _b, (2,)), ("gain_db", _f)], (2, WIRE_MAX_OUTPUTS)),
+    ("outputs", [("enabled", _b), ("mute", _b), ("reserved", _b, (2,)), ("gain_db", _f), ("delay_ms", _f)], (WIRE_MAX_OUTPUTS,)),
+    ("pins", [("num_pin_outputs", _b), ("pins", _b, (5,)), ("reserved", _b, (2,))]),
+    ("eq", [("type", _b), ("reserved", _b, (3,)), ("freq", _f), ("q", _f), ("gain_db", _f)], (WIRE_MAX_CHANNELS, MAX_BANDS)),
+    ("channel_names", "S32", (WIRE_MAX_CHANNELS,)),
+    ("i2s_config", [("output_types", _b, (4,)), ("bck_pin", _b), ("mck_pin", _b), ("mck_enabled", _b), ("mck_multiplier", _b), ("reserved", _b, (8,))]),
+    ("leveller", [("enabled", _b), ("speed", _b), ("lookahead", _b), ("reserved", _b), ("amount", _f), ("max_gain_db", _f), ("gate_threshold_db", _f)]),
+    ("preamp", [("preamp_db", _f, (2,)), ("reserved", _b, (8,))]),
+    ("master_volume", [("master_volume_db", _f), ("reserved", _b, (12,))]),
+])
+assert WIRE_BULK.itemsize == 2896
+
+XFEED_CFG = np.dtype({"names": ["enabled", "itd_enabled", "preset", "custom_fc", "custom_feed_db"], "formats": [_b, _b, _b, _f, _f],
+                      "offsets": [0, 1, 2, 4, 8], "itemsize": 12})
+LEV_CFG = np.dtype({"names": ["enabled", "amount", "speed", "max_gain_db", "lookahead", "gate_threshold_db"], "formats": [_b, _f, _b, _f, _b, _f],
+                    "offsets": [0, 4, 8, 12, 16, 20], "itemsize": 24})
+# dspi_bulk_state (include/dspi_b200.h): the globals bulk_params_apply() edits
+BULK_STATE = np.dtype({
+    "names": ["platform", "preamp_db", "preamp_linear", "preamp_q28", "master_volume_db", "master_volume_linear", "master_volume_q15",
+              "bypass_master_eq", "loudness_enabled", "loudness_ref_spl", "loudness_intensity_pct", "crossfeed", "leveller",
+              "legacy_gain_db", "legacy_gain_linear", "legacy_gain_mul", "legacy_mute", "channel_delays_ms", "crosspoints", "outputs", "recipes"],
+    "formats": [_i, (_f, (2,)), (_f, (2,)), (_i, (2,)), _f, _f, _i, _b, _b, _f, _f, XFEED_CFG, LEV_CFG,
+                (_f, (3,)), (_f, (3,)), (_i, (3,)), (_b, (3,)), (_f, (WIRE_MAX_CHANNELS,)), (CROSSPOINT, (2, WIRE_MAX_OUTPUTS)),
+                (OUTPUT, (WIRE_MAX_OUTPUTS,)), (EQ_PARAM, (WIRE_MAX_CHANNELS, MAX_BANDS))],
+    "offsets": [0, 4, 12, 20, 28, 32, 36, 40, 41, 44, 48, 52, 64, 88, 100, 112, 124, 128, 172, 388, 568],
+    "itemsize": 2680})

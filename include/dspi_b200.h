@@ -318,6 +318,72 @@ uint64_t dspi_chainq_launch_count(dspi_chainq *c);
 void dspi_crossfeed_compute_coefficients_q28(dspi_crossfeed_state_q28 *st, const dspi_crossfeed_config *cfg, float sample_rate);
 void dspi_loudness_compute_table_q28(dspi_loudness_coeffs_q28 table[61][2], float ref_spl, float intensity_pct, float sample_rate);
 
+/* ---- bulk parameter ingest (host side; SURVEY.md 8 f-1 / the dspi_set_bulk_params of 8 b) ------- */
+/* WireBulkParams, bulk_params.h:40-205: the 2896-byte little-endian packet the DSPi Console sends with
+ * REQ_SET_ALL_PARAMS and reads with REQ_GET_ALL_PARAMS.  Byte-identical layout. */
+#define DSPI_WIRE_MAX_CHANNELS 11
+#define DSPI_WIRE_MAX_OUTPUTS  9
+#define DSPI_WIRE_FORMAT_VERSION 6
+#define DSPI_PLATFORM_RP2040 0
+#define DSPI_PLATFORM_RP2350 1
+typedef struct __attribute__((packed)) {
+    struct __attribute__((packed)) { uint8_t format_version, platform_id, num_channels, num_output_channels, num_input_channels, max_bands;
+                                     uint16_t payload_length, fw_version_major, fw_version_minor; uint32_t reserved; } header;          /*  16 */
+    struct __attribute__((packed)) { float preamp_gain_db; uint8_t bypass, loudness_enabled, reserved[2];
+                                     float loudness_ref_spl, loudness_intensity_pct; } global;                                        /*  16 */
+    struct __attribute__((packed)) { uint8_t enabled, preset, itd_enabled, reserved; float custom_fc, custom_feed_db; uint32_t reserved2; } crossfeed;   /* 16 */
+    struct __attribute__((packed)) { float gain_db[3]; uint8_t mute[3], reserved; } legacy;                                           /*  16 */
+    struct __attribute__((packed)) { float delay_ms[DSPI_WIRE_MAX_CHANNELS]; } delays;                                                /*  44 */
+    struct __attribute__((packed)) { uint8_t enabled, phase_invert, reserved[2]; float gain_db; } crosspoints[2][DSPI_WIRE_MAX_OUTPUTS];   /* 144 */
+    struct __attribute__((packed)) { uint8_t enabled, mute, reserved[2]; float gain_db, delay_ms; } outputs[DSPI_WIRE_MAX_OUTPUTS];   /* 108 */
+    struct __attribute__((packed)) { uint8_t num_pin_outputs, pins[5], reserved[2]; } pins;                                           /*   8 */
+    struct __attribute__((packed)) { uint8_t type, reserved[3]; float freq, q, gain_db; } eq[DSPI_WIRE_MAX_CHANNELS][DSPI_MAX_BANDS]; /* 2112 */
+    char channel_names[DSPI_WIRE_MAX_CHANNELS][32];                                                                                    /* 352 */
+    struct __attribute__((packed)) { uint8_t output_types[4], bck_pin, mck_pin, mck_enabled, mck_multiplier, reserved[8]; } i2s_config;    /* 16 */
+    struct __attribute__((packed)) { uint8_t enabled, speed, lookahead, reserved; float amount, max_gain_db, gate_threshold_db; } leveller; /* 16 */
+    struct __attribute__((packed)) { float preamp_db[2]; uint8_t reserved[8]; } preamp;                                               /*  16 */
+    struct __attribute__((packed)) { float master_volume_db; uint8_t reserved[12]; } master_volume;                                   /*  16 */
+} dspi_wire_bulk_params;
+#ifdef __cplusplus
+static_assert(sizeof(dspi_wire_bulk_params) == 2896, "WireBulkParams");
+#else
+_Static_assert(sizeof(dspi_wire_bulk_params) == 2896, "WireBulkParams");
+#endif
+
+/* The globals bulk_params_apply() writes that feed the DSP path (bulk_params.c:22-43), for one device. */
+typedef struct {
+    int32_t platform;                        /* DSPI_PLATFORM_*: 11 channels / 9 outputs or 7 / 5                  */
+    float preamp_db[2], preamp_linear[2]; int32_t preamp_q28[2];          /* global_preamp_db / _linear / _mul     */
+    float master_volume_db, master_volume_linear; int32_t master_volume_q15;
+    uint8_t bypass_master_eq, loudness_enabled, reserved0[2];
+    float loudness_ref_spl, loudness_intensity_pct;
+    dspi_crossfeed_config crossfeed;
+    dspi_leveller_config leveller;
+    float legacy_gain_db[3], legacy_gain_linear[3]; int32_t legacy_gain_mul[3]; uint8_t legacy_mute[3], reserved1;
+    float channel_delays_ms[DSPI_WIRE_MAX_CHANNELS];
+    dspi_matrix_crosspoint crosspoints[2][DSPI_WIRE_MAX_OUTPUTS];        /* gain_linear by the firmware's db_to_linear */
+    dspi_output_channel outputs[DSPI_WIRE_MAX_OUTPUTS];                  /* delay_samples is filled by dspi_bulk_state_to_chain_* */
+    dspi_eq_param recipes[DSPI_WIRE_MAX_CHANNELS][DSPI_MAX_BANDS];       /* filter_recipes[][]                      */
+} dspi_bulk_state;
+
+/* power-on values of those globals (usb_audio.c:148-211, leveller.h:69-74, matrix defaults config.h) */
+void dspi_bulk_state_defaults(dspi_bulk_state *st, int platform);
+/* bulk_params_apply(), bulk_params.c:178-377, on `st` instead of the firmware's globals.  Same return codes:
+ * 0 ok, -1 format version, -2 platform, -3 channel counts, -4 payload length.  Gains go through the
+ * firmware's own db_to_linear (a 4-term Taylor series clamped to [-60, +20] dB, bulk_params.c:49-56;
+ * SURVEY quirk 2) unless exact_db != 0 (then 10^(dB/20)); master volume always uses powf (:361-374). */
+int dspi_bulk_params_apply(const dspi_wire_bulk_params *in, dspi_bulk_state *st, int exact_db);
+/* bulk_params_collect(), bulk_params.c:62-172 (pins, names and I2S sections are control plane: zero) */
+void dspi_bulk_params_collect(const dspi_bulk_state *st, dspi_wire_bulk_params *out);
+/* What the main loop derives after a successful apply (main.c:1137-1139 and the pending-flag handlers):
+ * dsp_recalculate_all_filters, dsp_update_delay_samples, loudness table + row for the host volume,
+ * crossfeed and leveller coefficients.  `previous` (may be NULL) supplies the filters whose state must
+ * survive (dsp_compute_coefficients only clears state on a topology flip). */
+int dspi_bulk_state_to_chain_f32(const dspi_bulk_state *st, float sample_rate, int16_t host_volume_8_8, int host_mute,
+                                 dspi_chain_params_f32 *params, dspi_biquad_f32 biquads[11][DSPI_MAX_BANDS]);
+int dspi_bulk_state_to_chain_q28(const dspi_bulk_state *st, float sample_rate, int16_t host_volume_8_8, int host_mute,
+                                 dspi_chain_params_q28 *params, dspi_biquad_q28 biquads[7][DSPI_MAX_BANDS]);
+
 /* ---- S/PDIF (IEC 60958) subframe encoder: the step after the chain -------------------------- */
 /* What stereo_to_spdif_producer_give_s32() does with every S/PDIF producer buffer
  * (pico_audio_spdif_multi/sample_encoding.cpp:42-50 -> spdif_update_subframe,

@@ -118,5 +118,40 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 
+
+
+def make_bulk():
+    """Fixture D "bulk": WireBulkParams packets and the states the reference's bulk_params_apply() leaves (both platforms)."""
+    import ctypes as C
+    from dspi_b200 import api
+    from tests.bulk_cases import wire_packet
+    from tests.orc import ORACLE_DIR
+    save = {}
+    for platform, key in ((L.PLATFORM_RP2350, "rp2350"), (L.PLATFORM_RP2040, "rp2040")):
+        ref = C.CDLL(os.path.join(ORACLE_DIR, "_ref", f"libdspi_ref_bulk_{key}.so"))
+        wires, states, rcs = [], [], []
+        for version in (2, 4, 5, 6, 6, 6):
+            w = wire_packet(platform, 700 + len(wires), version)
+            if len(wires) == 4:
+                w["header"][0]["payload_length"] = 64        # rejected: -4
+            st = api.bulk_state_defaults(platform)           # layout only; values come from the reference below
+            rcs.append(ref.ref_bulk_apply(w.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p)))
+            # the x86 object returns INT_MIN where the ARM firmware saturates (SURVEY quirk 7): store the ARM value
+            over = st["preamp_linear"] * np.float32(2.0 ** 28) >= np.float32(2.0 ** 31)
+            st["preamp_q28"][over & (st["preamp_q28"] == np.iinfo(np.int32).min)] = np.iinfo(np.int32).max
+            wires.append(w.copy())
+            states.append(st.copy())
+        # raw bytes: .npy headers cannot describe the padded C layouts
+        save[f"{key}_wire"] = np.frombuffer(b"".join(x.tobytes() for x in wires), np.uint8).reshape(len(wires), -1)
+        save[f"{key}_state"] = np.frombuffer(b"".join(x.tobytes() for x in states), np.uint8).reshape(len(states), -1)
+        save[f"{key}_rc"] = np.array(rcs, np.int32)
+    np.savez_compressed(os.path.join(HERE, "bulk.npz"), **save)
+    print("bulk.npz", os.path.getsize(os.path.join(HERE, "bulk.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--bulk" in sys.argv:
+        make_bulk()
+    else:
+        main()
+        make_bulk()
