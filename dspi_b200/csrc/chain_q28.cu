@@ -5,12 +5,11 @@
 // :1191-1276); fast_mul_q28 dsp_pipeline.c:47-58; fast_mul_q15 config.h:556-567; cascade
 // dsp_process_rp2040.S:225-394; crossfeed.c:161-180; leveller.c:275-389; PDM pdm_generator.c:351-397.
 //
-// Same decomposition as chain_f32.cu (front: 16 instances x {L,R} per warp with __shfl_xor(..,16)
-// for the stereo-linked leveller and the crossfeed mix; outputs: one output index x 32 instances per
-// warp; modulator: one instance per lane).  The EQ runs in the reference's own loop order — band
-// outer, the packet's samples inner — over a lane-private shared-memory column, loading the five
-// coefficients and two state words of a band once per packet from an SoA store in HBM; everything is
-// integer-pipe bound (≈ 27 integer ops per band-sample), so registers are kept low for occupancy.
+// Same stage-wise decomposition as chain_f32.cu: pre (unpack, preamp, loudness) -> K2 over the master rows
+// -> post (leveller, peaks, crossfeed) -> mix -> K2 over the output rows -> outpost (gain, delay, metering,
+// 24-bit words) -> ring update -> modulator, on three streams over packet slices.  The EQ rows run through
+// the Q28 cascade kernel of the EQ engine (eq_q28.cu: TMA ring, coefficients pre-split in registers);
+// everything is integer-pipe bound (about 27 integer ops per band-sample).
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -30,6 +29,7 @@ constexpr int kRoles = DSPI_CHAINQ_EQ_CHANNELS;
 constexpr int kMaxDelay = DSPI_CHAINQ_MAX_DELAY;
 constexpr int kLa = DSPI_LA_SAMPLES;
 constexpr int kPkt = DSPI_PACKET_MAX;
+constexpr int kXs = 33;                                       // shared-memory column stride: conflict-free for lane = instance AND lane = frame
 constexpr int32_t kUnity = 1 << 28;
 constexpr int32_t kClipThresh = (1 << 28) + 268;              // config.h:54
 
@@ -37,8 +37,7 @@ enum : uint8_t { F_BYPASS_MASTER = 1, F_LOUD = 2, F_XFEED = 4, F_LEV = 8, F_LOOK
 enum : uint8_t { O_ENABLED = 1, O_MUTE = 2, O_PAIR_OFF = 4 };
 
 struct ChainQ {
-    uint32_t N, N_pad, nb, max_frames;
-    int32_t *bq;                                   // [role][band 12][8][N_pad]: b0 b1 b2 a1 a2 s1 s2 bypass
+    uint32_t N, N_pad, nb, max_frames, ldF;        // ldF: row stride of mrow / orow / subq (frames, multiple of 4)
     int32_t *preamp;                               // [2][N_pad]
     uint8_t *flags;
     int32_t *loud_c; int32_t *loud_st; uint8_t *loud_byp;    // [2 j][5][N_pad], [2 side][2 j][2][N_pad], [N_pad]
@@ -48,7 +47,10 @@ struct ChainQ {
     int32_t *dline; uint32_t *widx_in, *widx_out;  // [5][N_pad][2048], [N_pad]
     int32_t *pdm;                                  // [9][N_pad]
     uint16_t *peaks; uint16_t *clip;               // [7][N_pad], [N_pad]
-    int32_t *master; int32_t *subq;                // [2][max_frames][N_pad], [max_frames][N_pad]
+    int32_t *mrow;                                 // [2 N_pad][ldF] master rows, row = side * N_pad + inst
+    int32_t *orow;                                 // [5 N_pad][ldF] output rows, row = o * N_pad + inst
+    int32_t *subq;                                 // [N_pad][ldF] Q28 sub samples for the modulator
+    uint8_t *skip_m, *skip_o;                      // [2 N_pad], [5 N_pad]: rows whose EQ is frozen (K2 row skip)
 };
 
 // fast_mul_q28(), dsp_pipeline.c:47-58: 32-bit wrapping, lo*lo partial product dropped
@@ -71,42 +73,6 @@ __device__ __forceinline__ int32_t mul_q15(int32_t s, int32_t g)
     return (int32_t)((hh << 17) + (mid << 1) + (ll >> 15));
 }
 
-struct QC { int32_t hi; uint32_t lo, hi16; };
-__device__ __forceinline__ QC qsplit(int32_t c) { QC r; r.hi = c >> 16; r.lo = (uint32_t)c & 0xFFFFu; r.hi16 = (uint32_t)r.hi << 4; return r; }
-__device__ __forceinline__ uint32_t mulq(const QC &c, int32_t xh, uint32_t xl)
-{
-    const uint32_t mid = (uint32_t)c.hi * xl + c.lo * (uint32_t)xh;
-    return c.hi16 * (uint32_t)xh + (uint32_t)((int32_t)mid >> 12);
-}
-
-// dsp_process_channel_block(), dsp_process_rp2040.S:225-394, over a lane-private column xs[i * 32]
-__device__ __forceinline__ void eq_packet(const ChainQ &d, uint32_t role, uint32_t inst, int32_t *xs, uint32_t n)
-{
-    const size_t Np = d.N_pad;
-    for (uint32_t b = 0; b < d.nb; b++) {
-        int32_t *base = d.bq + ((size_t)(role * DSPI_MAX_BANDS + b) * 8) * Np + inst;
-        if (base[7 * Np]) continue;                                           // bypass byte, .S:246-248
-        const QC c0 = qsplit(base[0]), c1 = qsplit(base[1 * Np]), c2 = qsplit(base[2 * Np]), c3 = qsplit(base[3 * Np]), c4 = qsplit(base[4 * Np]);
-        uint32_t s1 = (uint32_t)base[5 * Np], s2 = (uint32_t)base[6 * Np];
-#pragma unroll 4
-        for (uint32_t i = 0; i < n; i++) {
-            const uint32_t x = (uint32_t)xs[i * 32];
-            const int32_t xh = (int32_t)x >> 16;
-            const uint32_t xl = x & 0xFFFFu;
-            const uint32_t y = mulq(c0, xh, xl) + s1;                         // :273-285
-            const uint32_t t1 = mulq(c1, xh, xl), t3 = mulq(c2, xh, xl);      // :288-312
-            const int32_t yh = (int32_t)y >> 16;
-            const uint32_t yl = y & 0xFFFFu;
-            const uint32_t t2 = mulq(c3, yh, yl), t4 = mulq(c4, yh, yl);      // :319-348
-            s1 = (t1 - t2) + s2;                                              // :332-335
-            s2 = t3 - t4;                                                     // :351-353
-            xs[i * 32] = (int32_t)y;
-        }
-        base[5 * Np] = (int32_t)s1;
-        base[6 * Np] = (int32_t)s2;
-    }
-}
-
 // leveller.c:124-139 (plain float, the RP2040's soft-float never fuses)
 __device__ __forceinline__ float gain_computer(float x_db, float threshold, float ratio, float knee)
 {
@@ -121,33 +87,128 @@ __device__ __forceinline__ float gain_computer(float x_db, float threshold, floa
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 2)
-chainq_front_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F)
+// pre: PCM unpack + preamp (usb_audio.c:997-1015), loudness TDF2 shelves (:1018-1047) -> master rows
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+chainq_pre_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t f_begin, uint32_t f_end, uint32_t F)
 {
-    extern __shared__ int32_t smem_q[];                    // [warps][kPkt][32]
+    __shared__ int32_t tile_s[2][2][32][kXs];
+    __shared__ uint32_t pcm_s[2][2][32][49];              // per warp, double-buffered: 32 instances x 32 frames x <= 6 bytes (rows padded to 49 words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t side = lane >> 4;
-    const uint32_t wbase = (blockIdx.x * (blockDim.x >> 5) + warp) * 16;
-    if (wbase >= d.N_pad) return;
-    const uint32_t inst = wbase + (lane & 15);
+    const uint32_t inst0 = (blockIdx.x * 2 + warp) * 32;
+    if (inst0 >= d.N_pad) return;
+    const uint32_t inst = inst0 + lane;
     const bool live = inst < d.N;
-    int32_t *xs = smem_q + (size_t)warp * kPkt * 32 + lane;
     const size_t Np = d.N_pad;
+    int32_t (*tile)[32][kXs] = tile_s[warp];
 
-    const uint8_t flags = d.flags[inst];
-    const bool loud_on = flags & F_LOUD, lev_on = flags & F_LEV, xf_on = flags & F_XFEED;
-    const bool skip_master = flags & F_BYPASS_MASTER, lookahead = flags & F_LOOKAHEAD;
-    const int32_t preamp = d.preamp[side * Np + inst];
-
-    int32_t lc[2][5], ls[2][2];
+    const bool loud_on = d.flags[inst] & F_LOUD;
     const uint8_t loud_byp = d.loud_byp[inst];
+    int32_t lc[2][5], ls[2][2][2], preamp[2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
 #pragma unroll
         for (int k = 0; k < 5; k++) lc[j][k] = d.loud_c[(j * 5 + k) * Np + inst];
-        ls[j][0] = d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst];
-        ls[j][1] = d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            ls[side][j][0] = d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst];
+            ls[side][j][1] = d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst];
+        }
     }
+    preamp[0] = d.preamp[inst];
+    preamp[1] = d.preamp[Np + inst];
+    const uint32_t bpf = bit_depth == 24 ? 6u : 4u;
+    const bool words_ok = ((reinterpret_cast<uintptr_t>(pcm) | ((size_t)F * bpf) | ((size_t)f_begin * bpf)) & 3u) == 0;
+    const uint8_t *my_pcm = pcm + (size_t)inst * F * bpf;
+    const uint32_t n_inst = min(32u, d.N > inst0 ? d.N - inst0 : 0u);
+    auto fetch = [&](uint32_t f0, int buf) {               // see chain_pre_kernel (chain_f32.cu)
+        if (words_ok && f0 < f_end) {
+            const uint32_t nwords = (min(32u, f_end - f0) * bpf + 3) / 4;
+            for (uint32_t i = 0; i < n_inst; i++) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(pcm + ((size_t)(inst0 + i) * F + f0) * bpf);
+                for (uint32_t w = lane; w < nwords; w += 32) cp_async_4(&pcm_s[warp][buf][i][w], src + w);
+            }
+        }
+        cp_async_commit();
+    };
+    fetch(f_begin, 0);
+
+    int buf = 0;
+    for (uint32_t f0 = f_begin; f0 < f_end; f0 += 32, buf ^= 1) {
+        const uint32_t nv = min(32u, f_end - f0);
+        const uint8_t *tile_bytes = my_pcm + (size_t)f0 * bpf;
+        fetch(f0 + 32, buf ^ 1);
+        if (words_ok) {
+            cp_async_wait<1>();
+            __syncwarp();
+            tile_bytes = reinterpret_cast<const uint8_t *>(pcm_s[warp][buf][lane]);
+        }
+        for (uint32_t t = 0; t < nv; t++) {
+            const uint8_t *q = tile_bytes + (size_t)t * bpf;
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                int32_t raw = 0;
+                if (live) {
+                    if (bit_depth == 24) {
+                        const uint8_t *b = q + side * 3;
+                        raw = ((int32_t)((uint32_t)b[2] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[0] << 8)) >> 2;       // :1001
+                    } else {
+                        const uint8_t *b = q + side * 2;
+                        raw = (int32_t)((uint32_t)(int32_t)(int16_t)((uint16_t)b[0] | (uint16_t)b[1] << 8) << 14);       // :1010
+                    }
+                }
+                int32_t x = mul_q28(raw, preamp[side]);
+                if (loud_on) {
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        if ((loud_byp >> j) & 1) continue;
+                        const int32_t result = mul_q28(lc[j][0], x) + ls[side][j][0];                                    // :1026
+                        ls[side][j][0] = mul_q28(lc[j][1], x) - mul_q28(lc[j][3], result) + ls[side][j][1];
+                        ls[side][j][1] = mul_q28(lc[j][2], x) - mul_q28(lc[j][4], result);
+                        x = result;
+                    }
+                }
+                tile[side][t][lane] = x;
+            }
+        }
+        __syncwarp();
+        if ((uint32_t)lane < nv) {
+#pragma unroll 8
+            for (int r = 0; r < 64; r++) {
+                const int side = r >> 5, i = r & 31;
+                d.mrow[((size_t)side * Np + inst0 + i) * d.ldF + f0 + lane] = tile[side][lane][i];
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst] = ls[side][j][0];
+            d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst] = ls[side][j][1];
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// post: Q28 leveller (leveller.c:275-389), input peaks, crossfeed (crossfeed.c:161-180), per packet
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+chainq_post_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
+{
+    extern __shared__ int32_t smem_q[];                    // per warp: packet columns [fpp][33] + look-ahead reads [fpp][33]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t side = lane >> 4;
+    const uint32_t inst16 = (blockIdx.x * (blockDim.x >> 5) + warp) * 16;
+    if (inst16 >= d.N_pad) return;
+    const uint32_t inst = inst16 + (lane & 15);
+    const size_t Np = d.N_pad;
+    int32_t *xw = smem_q + (size_t)warp * 2 * fpp * kXs;
+    int32_t *xs = xw + lane;
+    int32_t *hs = xw + (size_t)fpp * kXs + lane;
+
+    const uint8_t flags = d.flags[inst];
+    const bool lev_on = flags & F_LEV, xf_on = flags & F_XFEED, lookahead = flags & F_LOOKAHEAD;
     const int32_t xf_a0 = d.xf[0 * Np + inst], xf_b1 = d.xf[1 * Np + inst], xf_ap = d.xf[4 * Np + inst];
     int32_t xf_lp = d.xf[(2 + side) * Np + inst], xf_as = d.xf[(5 + side) * Np + inst];
     float lvc[9];
@@ -159,36 +220,23 @@ chainq_front_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_dept
     uint32_t la_idx = d.lev_idx[inst];
     int32_t *la_buf = d.lev_la + (size_t)side * kLa * Np + inst;
 
-    const uint32_t bpf = bit_depth == 24 ? 6u : 4u;
-    const uint8_t *my_pcm = pcm + ((size_t)inst * F) * bpf + side * (bpf / 2);
     int32_t peak_last = 0;
     uint16_t clip = 0;
-
     for (uint32_t p = p0; p < p0 + n_packets; p++) {
         const uint32_t f0 = p * fpp;
-        // PASS 1 (:997-1015) + loudness (:1018-1047)
-        for (uint32_t i = 0; i < fpp; i++) {
-            int32_t raw = 0;
-            if (live) {
-                const uint8_t *q = my_pcm + (size_t)(f0 + i) * bpf;
-                if (bit_depth == 24) raw = ((int32_t)((uint32_t)q[2] << 24 | (uint32_t)q[1] << 16 | (uint32_t)q[0] << 8)) >> 2;    // :1001
-                else raw = (int32_t)((uint32_t)(int32_t)(int16_t)((uint16_t)q[0] | (uint16_t)q[1] << 8) << 14);                   // :1010
+        if (lev_on && lookahead) {                                            // see chain_post_kernel (chain_f32.cu)
+            uint32_t idx = la_idx;
+            for (uint32_t i = 0; i < fpp; i++) {
+                cp_async_4(hs + i * kXs, la_buf + (size_t)idx * Np);
+                if (++idx >= (uint32_t)kLa) idx = 0;
             }
-            int32_t x = mul_q28(raw, preamp);
-            if (loud_on) {
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    if ((loud_byp >> j) & 1) continue;
-                    const int32_t result = mul_q28(lc[j][0], x) + ls[j][0];                              // :1026
-                    ls[j][0] = mul_q28(lc[j][1], x) - mul_q28(lc[j][3], result) + ls[j][1];
-                    ls[j][1] = mul_q28(lc[j][2], x) - mul_q28(lc[j][4], result);
-                    x = result;
-                }
-            }
-            xs[i * 32] = x;
         }
-        // PASS 2 (:1050-1055)
-        if (!skip_master) eq_packet(d, side, inst, xs, fpp);
+        for (int r = 0; r < 32; r++) {
+            const int32_t *row = d.mrow + ((size_t)(r >> 4) * Np + inst16 + (r & 15)) * d.ldF + f0;
+            for (uint32_t t = lane; t < fpp; t += 32) cp_async_4(xw + t * kXs + r, row + t);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
         __syncwarp();
 
         // PASS 2.5: leveller (leveller.c:275-389); every lane walks the same shuffles
@@ -197,7 +245,7 @@ chainq_front_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_dept
             const int32_t one_minus = kUnity - a_rms;
             int32_t e = env;
             for (uint32_t i = 0; i < fpp; i++) {                                                         // :292-299
-                const int32_t s = xs[i * 32];
+                const int32_t s = xs[i * kXs];
                 const int32_t sq = mul_q28(s, s);
                 e = mul_q28(a_rms, e) + mul_q28(one_minus, sq);
             }
@@ -219,13 +267,19 @@ chainq_front_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_dept
             const float gl = (float)pow(10.0, (double)__fdiv_rn(new_smooth, 20.0f));                      // :332
             const int32_t g_cur = __float2int_rz(__fmul_rn(gl, 268435456.0f));                            // :334 (saturating)
             const int32_t g_prev = gain_q;
+            // :352 divides a 64-bit product by (fpp - 1) per sample.  |product| < 2^39 and the divisor is < 192, so the
+            // correctly rounded double quotient can never cross an integer (it is at least 1/191 away from the next one
+            // unless exact, the rounding error is below 2^-13): truncating it IS the int64 quotient, without the
+            // ~100-instruction 64-bit division routine in the per-sample loop.
+            const double inv_den = fpp > 1 ? (double)(int32_t)(fpp - 1) : 1.0;
+            const double g_diff = (double)(int32_t)((uint32_t)g_cur - (uint32_t)g_prev);            // the int32 difference of :352
             for (uint32_t i = 0; i < fpp; i++) {                                                          // :347-386
                 int32_t gain;
                 if (fpp == 1) gain = g_cur;
-                else gain = g_prev + (int32_t)(((int64_t)(g_cur - g_prev) * (int64_t)i) / (int32_t)(fpp - 1));   // :352
-                int32_t o = xs[i * 32];
+                else gain = g_prev + (int32_t)(int64_t)__ddiv_rn(g_diff * (double)i, inv_den);           // :352
+                int32_t o = xs[i * kXs];
                 if (lev_on && lookahead) {
-                    const int32_t held = la_buf[(size_t)la_idx * Np];
+                    const int32_t held = hs[i * kXs];
                     la_buf[(size_t)la_idx * Np] = o;
                     o = held;
                     la_idx++;
@@ -243,7 +297,7 @@ chainq_front_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_dept
                         if (max_g < gain) gain = (max_g > kUnity) ? max_g : kUnity;
                     }
                 }
-                if (lev_on) xs[i * 32] = mul_q28(o, gain);
+                if (lev_on) xs[i * kXs] = mul_q28(o, gain);
             }
             if (lev_on) {
                 env = e;
@@ -255,9 +309,8 @@ chainq_front_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_dept
 
         // PASS 3 (:1065-1073)
         int32_t pk = 0;
-        int32_t *mout = d.master + ((size_t)side * d.max_frames + f0) * Np + inst;
         for (uint32_t i = 0; i < fpp; i++) {
-            int32_t v = xs[i * 32];
+            int32_t v = xs[i * kXs];
             const int32_t a = abs(v);
             if (a > pk) pk = a;
             int32_t lp = 0, ap = 0;
@@ -269,18 +322,19 @@ chainq_front_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_dept
             }
             const int32_t ap_other = __shfl_xor_sync(0xffffffffu, ap, 16);
             if (xf_on) v = (v - lp) + ap_other;                                                           // :178-179
-            mout[(size_t)i * Np] = v;
+            xs[i * kXs] = v;
         }
         peak_last = pk;
         if (pk > kClipThresh) clip |= (uint16_t)(1u << side);
         __syncwarp();
+        for (uint32_t t = lane; t < fpp; t += 32) {
+#pragma unroll 8
+            for (int r = 0; r < 32; r++)
+                d.mrow[((size_t)(r >> 4) * Np + inst16 + (r & 15)) * d.ldF + f0 + t] = xw[t * kXs + r];
+        }
+        __syncwarp();
     }
 
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-        d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst] = ls[j][0];
-        d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst] = ls[j][1];
-    }
     d.xf[(2 + side) * Np + inst] = xf_lp;
     d.xf[(5 + side) * Np + inst] = xf_as;
     d.lev_i[side * Np + inst] = env;
@@ -296,136 +350,193 @@ chainq_front_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_dept
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 2)
-chainq_out_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F, int32_t *__restrict__ spdif_out)
+// matrix mix in Q15 (usb_audio.c:1076-1100): lane = frame
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+chainq_mix_kernel(ChainQ d, uint32_t f_begin, uint32_t f_end)
 {
-    extern __shared__ int32_t smem_q[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t wid = blockIdx.x * (blockDim.x >> 5) + warp;
-    const uint32_t groups = d.N_pad / 32;
-    if (wid >= groups * kOuts) return;
-    const uint32_t o = wid / groups;
-    const uint32_t inst = (wid % groups) * 32 + lane;
-    const bool live = inst < d.N;
+    const int lane = threadIdx.x & 31;
+    constexpr int kB = 4;
+    const uint32_t n_tiles = (f_end - f_begin + 32 * kB - 1) / (32 * kB);
+    const uint64_t units = (uint64_t)d.N * n_tiles;
     const size_t Np = d.N_pad;
-    int32_t *ys = smem_q + (size_t)warp * kPkt * 32 + lane;
-
-    const uint8_t of = d.o_flags[o * Np + inst];
-    const bool enabled = of & O_ENABLED, mute = of & O_MUTE, pair_off = of & O_PAIR_OFF;
-    const int32_t gl = d.o_gl[o * Np + inst], gr = d.o_gr[o * Np + inst], gain = d.o_gain[o * Np + inst];
-    const int32_t dly = d.o_dly[o * Np + inst];
-    const uint8_t iflags = d.flags[inst];
-    const bool any_delay = iflags & F_ANY_DELAY, delay_on = any_delay && dly > 0;
-    const bool run_eq = enabled && !mute && !(iflags & F_BYPASS_MASTER);                                  // :1197-1201 (quirk: gated on bypass_master_eq)
-    uint32_t widx = d.widx_in[inst];
-    int32_t *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;
-    const bool is_sub = o == kOuts - 1;
-    int32_t *my_spdif = nullptr;
-    if (!is_sub && spdif_out && live) my_spdif = spdif_out + (((size_t)inst * 2 + (o >> 1)) * F) * 2 + (o & 1);
-
-    int32_t peak_last = 0;
-    uint16_t clip = 0;
-    for (uint32_t p = p0; p < p0 + n_packets; p++) {
-        const uint32_t f0 = p * fpp;
-        // PASS 4 (:1076-1100)
-        for (uint32_t i = 0; i < fpp; i++) {
-            int32_t v = 0;
-            if (enabled) {
-                const int32_t l = d.master[((size_t)0 * d.max_frames + f0 + i) * Np + inst];
-                const int32_t r = d.master[((size_t)1 * d.max_frames + f0 + i) * Np + inst];
-                if (gl != 0 && gr != 0) v = mul_q15(l, gl) + mul_q15(r, gr);
-                else if (gl != 0) v = mul_q15(l, gl);
-                else if (gr != 0) v = mul_q15(r, gr);
-            }
-            ys[i * 32] = v;
+    for (uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t inst = (uint32_t)(u / n_tiles), tile = (uint32_t)(u % n_tiles);
+        const uint32_t fbase = f_begin + tile * 32 * kB + lane;
+        int32_t l[kB], r[kB];
+#pragma unroll
+        for (int j = 0; j < kB; j++) {
+            const uint32_t f = fbase + 32 * j;
+            l[j] = f < f_end ? d.mrow[(size_t)inst * d.ldF + f] : 0;
+            r[j] = f < f_end ? d.mrow[(Np + inst) * d.ldF + f] : 0;
         }
-        // PASS 5 (:1196-1213)
-        if (run_eq) eq_packet(d, 2 + o, inst, ys, fpp);
-        int32_t pk = 0;
-        for (uint32_t t0 = 0; t0 < fpp; t0 += 8) {
-            const int nvalid = min(8, (int)(fpp - t0));
-            int32_t x[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                x[i] = (i < nvalid) ? ys[(t0 + i) * 32] : 0;
-                if (enabled) x[i] = (gain == 0) ? 0 : mul_q15(x[i], gain);                                // :1206-1212
-            }
-            if (delay_on) {                                                                               // PASS 6 (:1216-1230)
-                if (dly <= kMaxDelay - 8) {
+        for (int o = 0; o < kOuts; o++) {
+            const bool enabled = d.o_flags[o * Np + inst] & O_ENABLED;
+            const int32_t gl = d.o_gl[o * Np + inst], gr = d.o_gr[o * Np + inst];
 #pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if (i < nvalid) ring[(widx + t0 + i) & (kMaxDelay - 1)] = x[i];
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if (i < nvalid) x[i] = ring[(widx + t0 + i - (uint32_t)dly) & (kMaxDelay - 1)];
-                } else {
-                    for (int i = 0; i < nvalid; i++) {
-                        ring[(widx + t0 + i) & (kMaxDelay - 1)] = x[i];
-                        x[i] = ring[(widx + t0 + i - (uint32_t)dly) & (kMaxDelay - 1)];
-                    }
+            for (int j = 0; j < kB; j++) {
+                int32_t v = 0;
+                if (enabled) {
+                    if (gl != 0 && gr != 0) v = mul_q15(l[j], gl) + mul_q15(r[j], gr);
+                    else if (gl != 0) v = mul_q15(l[j], gl);
+                    else if (gr != 0) v = mul_q15(r[j], gr);
                 }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (i >= nvalid) break;
-                const int32_t v = x[i];
-                const int32_t a = abs(v);
-                if (a > pk) pk = a;
-                if (is_sub) {
-                    if (enabled) d.subq[(size_t)(f0 + t0 + i) * Np + inst] = v;                           // :1270 pdm_push_sample(buf_out[pdm_out][i])
-                } else if (my_spdif) {
-                    int32_t word = 0;
-                    if (!pair_off) {
-                        word = (v + 32) >> 6;                                                            // :1254-1255
-                        word = word > 0x7FFFFF ? 0x7FFFFF : (word < -0x800000 ? -0x800000 : word);        // clip_s24, config.h:547-551
-                    }
-                    my_spdif[(size_t)(f0 + t0 + i) * 2] = word;
-                }
+                const uint32_t f = fbase + 32 * j;
+                if (f < f_end) d.orow[((size_t)o * Np + inst) * d.ldF + f] = v;
             }
         }
-        if (any_delay) widx = (widx + fpp) & (kMaxDelay - 1);
-        peak_last = pk;
-        if (pk > kClipThresh && (!is_sub || enabled)) clip |= 1;
-        __syncwarp();
     }
-    uint16_t pq = (uint16_t)(peak_last >> 13);                                                            // :1239 / :1267
-    if (is_sub && !enabled) pq = 0;                                                                       // :1273
-    d.peaks[(2 + o) * Np + inst] = pq;
-    if (clip) atomicOr(reinterpret_cast<unsigned int *>(d.clip + (inst & ~1u)), (1u << (2 + o)) << (16 * (inst & 1)));
-    if (o == 0) d.widx_out[inst] = widx;
 }
 
-__global__ void __launch_bounds__(64)
+// ---------------------------------------------------------------------------------------------
+// outputs after the EQ: gain (:1203-1212), delay (:1216-1230), peaks (:1232-1241), 24-bit words (:1243-1257), sub (:1259-1275)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t outq_gain(int32_t v, bool enabled, int32_t gain)
+{
+    if (enabled) v = (gain == 0) ? 0 : mul_q15(v, gain);
+    return v;
+}
+
+struct OutCfgQ {
+    bool enabled, pair_off, delay_on;
+    int32_t gain;
+    uint32_t dl;                       // delay & (MAX - 1): MAX aliases to 0 (SURVEY a-10)
+    const int32_t *row;
+    const int32_t *ring;
+};
+
+__device__ __forceinline__ OutCfgQ outq_cfg(const ChainQ &d, uint32_t o, uint32_t inst, bool any_delay)
+{
+    OutCfgQ c;
+    const size_t Np = d.N_pad;
+    const uint8_t of = d.o_flags[o * Np + inst];
+    const int32_t dly = d.o_dly[o * Np + inst];
+    c.enabled = of & O_ENABLED;
+    c.pair_off = of & O_PAIR_OFF;
+    c.gain = d.o_gain[o * Np + inst];
+    c.delay_on = any_delay && dly > 0;
+    c.dl = (uint32_t)dly & (kMaxDelay - 1);
+    c.row = d.orow + ((size_t)o * Np + inst) * d.ldF;
+    c.ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;
+    return c;
+}
+
+// frame T of the call emits the post-gain sample of frame T - dl: inside the call from the output rows,
+// before it from the ring (see chain_f32.cu)
+__device__ __forceinline__ int32_t outq_sample(const OutCfgQ &c, uint32_t T, uint32_t widx0)
+{
+    if (!c.delay_on) return outq_gain(c.row[T], c.enabled, c.gain);
+    if (T >= c.dl) return outq_gain(c.row[T - c.dl], c.enabled, c.gain);
+    return c.ring[(widx0 + T - c.dl) & (kMaxDelay - 1)];
+}
+
+__device__ __forceinline__ int32_t clip_s24(int32_t w) { return w > 0x7FFFFF ? 0x7FFFFF : (w < -0x800000 ? -0x800000 : w); }   // config.h:547-551
+
+__global__ void __launch_bounds__(256)
+chainq_outpost_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp, uint32_t F, int32_t *__restrict__ spdif_out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t units = (uint64_t)d.N * n_packets;
+    const size_t Np = d.N_pad;
+    constexpr int kPairs = (kOuts - 1) / 2;
+    for (uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t inst = (uint32_t)(u / n_packets), p = p0 + (uint32_t)(u % n_packets);
+        const uint32_t f0 = p * fpp;
+        const bool last = p == p0 + n_packets - 1;
+        const bool any_delay = d.flags[inst] & F_ANY_DELAY;
+        const uint32_t widx0 = d.widx_in[inst];
+        unsigned int clip = 0;
+        for (int k = 0; k <= kPairs; k++) {                                   // the S/PDIF pairs, then the sub alone
+            const bool is_sub = k == kPairs;
+            const uint32_t oa = 2 * k, ob = is_sub ? oa : oa + 1;
+            const OutCfgQ ca = outq_cfg(d, oa, inst, any_delay), cb = outq_cfg(d, ob, inst, any_delay);
+            int32_t pka = 0, pkb = 0;
+            constexpr int kB = 4;
+            for (uint32_t tb = lane; tb < fpp; tb += 32 * kB) {
+                int32_t xa[kB], xb[kB];
+#pragma unroll
+                for (int j = 0; j < kB; j++) {
+                    const uint32_t t = tb + 32 * j;
+                    xa[j] = t < fpp ? outq_sample(ca, f0 + t, widx0) : 0;
+                    xb[j] = (!is_sub && t < fpp) ? outq_sample(cb, f0 + t, widx0) : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < kB; j++) {
+                    const uint32_t t = tb + 32 * j, T = f0 + t;
+                    if (t >= fpp) break;
+                    const int32_t aa = abs(xa[j]), ab = abs(xb[j]);
+                    if (aa > pka) pka = aa;
+                    if (ab > pkb) pkb = ab;
+                    if (is_sub) {
+                        if (ca.enabled) d.subq[(size_t)inst * d.ldF + T] = xa[j];                          // :1270 pdm_push_sample(buf_out[pdm_out][i])
+                    } else if (spdif_out) {
+                        int2 w = make_int2(0, 0);
+                        if (!ca.pair_off) { w.x = clip_s24((xa[j] + 32) >> 6); w.y = clip_s24((xb[j] + 32) >> 6); }   // :1254-1255
+                        *reinterpret_cast<int2 *>(spdif_out + (((size_t)inst * kPairs + k) * F + T) * 2) = w;
+                    }
+                }
+            }
+            // the reference compares signed values (`if (a > pk)`), so INT_MIN from abs(INT_MIN) never wins: plain signed max
+            pka = __reduce_max_sync(0xffffffffu, pka);
+            pkb = __reduce_max_sync(0xffffffffu, pkb);
+            if (lane == 0) {
+                if (last) {
+                    uint16_t pq = (uint16_t)(pka >> 13);                                                  // :1239 / :1267
+                    if (is_sub && !ca.enabled) pq = 0;                                                    // :1273
+                    d.peaks[(2 + oa) * Np + inst] = pq;
+                    if (!is_sub) d.peaks[(2 + ob) * Np + inst] = (uint16_t)(pkb >> 13);
+                }
+                if (pka > kClipThresh && (!is_sub || ca.enabled)) clip |= 1u << (2 + oa);
+                if (!is_sub && pkb > kClipThresh) clip |= 1u << (2 + ob);
+            }
+        }
+        if (lane == 0 && clip) atomicOr(reinterpret_cast<unsigned int *>(d.clip + (inst & ~1u)), clip << (16 * (inst & 1)));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+chainq_ring_kernel(ChainQ d, uint32_t F)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t units = (uint64_t)d.N * kOuts;
+    const size_t Np = d.N_pad;
+    for (uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t inst = (uint32_t)(u / kOuts), o = (uint32_t)(u % kOuts);
+        const bool any_delay = d.flags[inst] & F_ANY_DELAY;
+        const uint32_t widx0 = d.widx_in[inst];
+        const OutCfgQ c = outq_cfg(d, o, inst, any_delay);
+        if (c.delay_on) {
+            int32_t *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;
+            for (uint32_t T = (F > (uint32_t)kMaxDelay ? F - kMaxDelay : 0u) + lane; T < F; T += 32)
+                ring[(widx0 + T) & (kMaxDelay - 1)] = outq_gain(c.row[T], c.enabled, c.gain);
+        }
+        if (o == 0 && lane == 0) d.widx_out[inst] = any_delay ? (widx0 + F) & (kMaxDelay - 1) : widx0;
+    }
+}
+
+__global__ void __launch_bounds__(128)
 chainq_pdm_kernel(ChainQ d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
     const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= d.N) return;
     if (!(d.flags[inst] & F_SUB_ON)) return;                                                              // usb_audio.c:1261
-    pdm_modulate_frames(d.pdm, d.subq + inst, d.N_pad, d.N_pad, inst, f_begin, f_end, F, pdm_out);
+    pdm_modulate_frames(d.pdm, d.subq + (size_t)inst * d.ldF, 1, d.N_pad, inst, f_begin, f_end, F, pdm_out);
 }
 
-// filters[][] of n instances (instance-major AoS, 32-byte records) <-> [role][band][8][N_pad]
-__global__ void chainq_pack_kernel(const dspi_biquad_q28 *__restrict__ aos, uint32_t inst0, uint32_t n, ChainQ d)
+// filters[][] of n instances (instance-major AoS, 32-byte records) <-> the mirrors of the two EQ engines
+__global__ void chainq_scatter_kernel(const dspi_biquad_q28 *__restrict__ aos, uint32_t inst0, uint32_t n, uint32_t Np, dspi_biquad_q28 *__restrict__ m_aos,
+                                      dspi_biquad_q28 *__restrict__ o_aos, int to_mirrors)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * kRoles * DSPI_MAX_BANDS) return;
-    const uint32_t inst = inst0 + i / (kRoles * DSPI_MAX_BANDS), rb = i % (kRoles * DSPI_MAX_BANDS);
-    const dspi_biquad_q28 &q = aos[(size_t)inst * kRoles * DSPI_MAX_BANDS + rb];
-    int32_t *dst = d.bq + ((size_t)rb * 8) * d.N_pad + inst;
-    const size_t Np = d.N_pad;
-    dst[0] = q.b0; dst[1 * Np] = q.b1; dst[2 * Np] = q.b2; dst[3 * Np] = q.a1; dst[4 * Np] = q.a2;
-    dst[5 * Np] = q.s1; dst[6 * Np] = q.s2; dst[7 * Np] = q.bypass ? 1 : 0;
+    const uint32_t b = i % DSPI_MAX_BANDS, role = (i / DSPI_MAX_BANDS) % kRoles, inst = inst0 + i / (DSPI_MAX_BANDS * kRoles);
+    dspi_biquad_q28 *chain_q = const_cast<dspi_biquad_q28 *>(aos) + ((size_t)inst * kRoles + role) * DSPI_MAX_BANDS + b;
+    dspi_biquad_q28 *eng_q = role < 2 ? m_aos + ((size_t)role * Np + inst) * DSPI_MAX_BANDS + b : o_aos + ((size_t)(role - 2) * Np + inst) * DSPI_MAX_BANDS + b;
+    if (to_mirrors) *eng_q = *chain_q;
+    else *chain_q = *eng_q;
 }
-__global__ void chainq_unpack_kernel(dspi_biquad_q28 *__restrict__ aos, uint32_t inst0, uint32_t n, ChainQ d)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * kRoles * DSPI_MAX_BANDS) return;
-    const uint32_t inst = inst0 + i / (kRoles * DSPI_MAX_BANDS), rb = i % (kRoles * DSPI_MAX_BANDS);
-    dspi_biquad_q28 &q = aos[(size_t)inst * kRoles * DSPI_MAX_BANDS + rb];
-    const int32_t *src = d.bq + ((size_t)rb * 8) * d.N_pad + inst;
-    q.s1 = src[5 * (size_t)d.N_pad];
-    q.s2 = src[6 * (size_t)d.N_pad];
-}
+
 __global__ void chainq_status_kernel(ChainQ d, dspi_status_q28 *__restrict__ out)
 {
     const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
@@ -483,6 +594,7 @@ struct dspi_chainq {
     cudaStream_t stream;                  // the engine stream callers see; stages run on st.* between ev_begin and ev_done
     dspi::ChainStreams st;
     dspi_biquad_q28 *d_aos;
+    dspi_eq *eq_m, *eq_o;            // K2 engines over the master rows (2 N_pad channels) and the output rows (5 N_pad)
     std::vector<void *> allocs;
     uint64_t launches;
     void *d_pcm; size_t pcm_bytes;
@@ -536,6 +648,8 @@ int dspi_chainq_destroy(dspi_chainq *c)
     cudaSetDevice(c->desc.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     c->st.destroy();
+    if (c->eq_m) dspi_eq_destroy(c->eq_m);
+    if (c->eq_o) dspi_eq_destroy(c->eq_o);
     for (void *p : c->allocs) cudaFree(p);
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_spdif) cudaFree(c->d_spdif);
@@ -564,6 +678,7 @@ int dspi_chainq_create(dspi_chainq **out, const dspi_chain_desc *desc)
     if (!c) return fail(DSPI_ENOMEM, "host allocation failed");
     c->stream = nullptr;
     c->st = dspi::ChainStreams();
+    c->eq_m = c->eq_o = nullptr;
     c->d_aos = nullptr; c->launches = 0; c->d_pcm = nullptr; c->pcm_bytes = 0; c->d_spdif = nullptr; c->spdif_bytes = 0;
     c->d_pdmout = nullptr; c->pdmout_bytes = 0; c->d_status = nullptr;
     c->desc = *desc;
@@ -573,12 +688,22 @@ int dspi_chainq_create(dspi_chainq **out, const dspi_chain_desc *desc)
     d.N_pad = (d.N + 31) / 32 * 32;
     d.nb = desc->n_bands;
     d.max_frames = desc->max_frames;
+    d.ldF = (d.max_frames + 3u) & ~3u;
     const size_t Np = d.N_pad;
+    {
+        dspi_eq_desc ed;
+        memset(&ed, 0, sizeof(ed));
+        ed.arith = DSPI_ARITH_Q28; ed.n_bands = desc->n_bands; ed.device = desc->device;
+        ed.n_channels = 2 * d.N_pad;
+        int rc = dspi_eq_create(&c->eq_m, &ed);
+        ed.n_channels = dspi::kOuts * d.N_pad;
+        if (rc == DSPI_OK) rc = dspi_eq_create(&c->eq_o, &ed);
+        if (rc != DSPI_OK) { dspi_chainq_destroy(c); return rc; }
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = c->st.create();
 #define TRY(x) if (e == cudaSuccess) e = (x)
     TRY(dev_alloc(c, &c->d_aos, Np * dspi::kRoles * DSPI_MAX_BANDS));
-    TRY(dev_alloc(c, &d.bq, Np * dspi::kRoles * DSPI_MAX_BANDS * 8));
     TRY(dev_alloc(c, &d.preamp, 2 * Np));
     TRY(dev_alloc(c, &d.flags, Np));
     TRY(dev_alloc(c, &d.loud_c, 10 * Np));
@@ -601,15 +726,24 @@ int dspi_chainq_create(dspi_chainq **out, const dspi_chain_desc *desc)
     TRY(dev_alloc(c, &d.pdm, 9 * Np));
     TRY(dev_alloc(c, &d.peaks, dspi::kRoles * Np));
     TRY(dev_alloc(c, &d.clip, Np));
-    TRY(dev_alloc(c, &d.master, (size_t)2 * d.max_frames * Np, false));
-    TRY(dev_alloc(c, &d.subq, (size_t)d.max_frames * Np, false));
+    TRY(dev_alloc(c, &d.mrow, (size_t)2 * Np * d.ldF));
+    TRY(dev_alloc(c, &d.orow, (size_t)dspi::kOuts * Np * d.ldF));
+    TRY(dev_alloc(c, &d.subq, (size_t)Np * d.ldF));
+    TRY(dev_alloc(c, &d.skip_m, 2 * Np));
+    TRY(dev_alloc(c, &d.skip_o, dspi::kOuts * Np));
     TRY(dev_alloc(c, &c->d_status, Np));
     // every band of every channel starts bypassed (dsp_init_default_filters, dsp_pipeline.c:177-199)
     if (e == cudaSuccess) {
-        std::vector<int32_t> ones(Np, 1);
-        for (int rb = 0; rb < dspi::kRoles * DSPI_MAX_BANDS && e == cudaSuccess; rb++)
-            e = cudaMemcpyAsync(d.bq + ((size_t)rb * 8 + 7) * Np, ones.data(), Np * 4, cudaMemcpyHostToDevice, c->stream);
+        std::vector<dspi_biquad_q28> byp(Np * dspi::kRoles * DSPI_MAX_BANDS);
+        memset(byp.data(), 0, byp.size() * sizeof(dspi_biquad_q28));
+        for (auto &q : byp) q.bypass = 1;
+        e = cudaMemcpyAsync(dspi::eq_aos_mirror(c->eq_m), byp.data(), 2 * Np * DSPI_MAX_BANDS * sizeof(dspi_biquad_q28), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dspi::eq_aos_mirror(c->eq_o), byp.data(), dspi::kOuts * Np * DSPI_MAX_BANDS * sizeof(dspi_biquad_q28), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_aos, byp.data(), byp.size() * sizeof(dspi_biquad_q28), cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess && (dspi::eq_pack_range(c->eq_m, 0, 2 * d.N_pad, c->stream) || dspi::eq_pack_range(c->eq_o, 0, dspi::kOuts * d.N_pad, c->stream)))
+            e = cudaErrorUnknown;
     }
     TRY(init_states(c));
 #undef TRY
@@ -641,7 +775,7 @@ int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dsp
     const int O = dspi::kOuts;
     std::vector<int32_t> preamp(2 * n), loud_c(10 * n), xf(7 * n), gl(O * n), gr(O * n), gain(O * n), dly(O * n);
     std::vector<float> lev_c(9 * n);
-    std::vector<uint8_t> flags(n), loud_byp(n), oflags(O * n);
+    std::vector<uint8_t> flags(n), loud_byp(n), oflags(O * n), skip_m(2 * n), skip_o(O * n);
     for (uint32_t i = 0; i < n; i++) {
         const dspi_chain_params_q28 &p = params[i];
         int32_t vol_mul = p.host_mute ? 0 : (int32_t)p.host_vol_mul;                                    // usb_audio.c:975
@@ -662,6 +796,7 @@ int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dsp
             uint8_t f = (oc.enabled ? dspi::O_ENABLED : 0) | (oc.mute ? dspi::O_MUTE : 0);
             if (o < O - 1 && !oc.enabled && !p.matrix.outputs[o ^ 1].enabled) f |= dspi::O_PAIR_OFF;    // :1248-1251
             oflags[o * n + i] = f;
+            skip_o[o * n + i] = (oc.enabled && !oc.mute && !p.bypass_master_eq) ? 0 : 1;                 // :1197-1201 (quirk: gated on bypass_master_eq too)
             int32_t ds = oc.delay_samples;
             if (ds > DSPI_CHAINQ_MAX_DELAY) ds = DSPI_CHAINQ_MAX_DELAY;
             if (ds < 0) ds = 0;
@@ -672,6 +807,7 @@ int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dsp
                    (p.crossfeed_enabled ? dspi::F_XFEED : 0) | (p.leveller_enabled ? dspi::F_LEV : 0) |
                    (p.leveller_lookahead ? dspi::F_LOOKAHEAD : 0) | (any_delay ? dspi::F_ANY_DELAY : 0) |
                    (p.matrix.outputs[O - 1].enabled ? dspi::F_SUB_ON : 0);
+        skip_m[0 * n + i] = skip_m[1 * n + i] = p.bypass_master_eq ? 1 : 0;                              // :1050-1055
         loud_byp[i] = (p.loudness[0].bypass ? 1 : 0) | (p.loudness[1].bypass ? 2 : 0);
         for (int j = 0; j < 2; j++) {
             const int32_t v[5] = { p.loudness[j].b0, p.loudness[j].b1, p.loudness[j].b2, p.loudness[j].a1, p.loudness[j].a2 };
@@ -698,8 +834,12 @@ int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dsp
     CU_OK(put(d.o_gain, gain.data(), O, 4));
     CU_OK(put(d.o_flags, oflags.data(), O, 1));
     CU_OK(put(d.o_dly, dly.data(), O, 4));
+    CU_OK(put(d.skip_m, skip_m.data(), 2, 1));
+    CU_OK(put(d.skip_o, skip_o.data(), O, 1));
     CU_OK(cudaStreamSynchronize(c->stream));
-    return DSPI_OK;
+    int rc = dspi::eq_set_skip(c->eq_m, d.skip_m, c->stream);
+    if (rc == DSPI_OK) rc = dspi::eq_set_skip(c->eq_o, d.skip_o, c->stream);
+    return rc;
 }
 
 int dspi_chainq_upload_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, const dspi_biquad_q28 *biquads)
@@ -710,9 +850,16 @@ int dspi_chainq_upload_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, const
     CU_OK(cudaSetDevice(c->desc.device));
     const size_t row = (size_t)dspi::kRoles * DSPI_MAX_BANDS;
     CU_OK(cudaMemcpyAsync(c->d_aos + inst0 * row, biquads, n * row * sizeof(dspi_biquad_q28), cudaMemcpyHostToDevice, c->stream));
-    dspi::chainq_pack_kernel<<<(n * row + 127) / 128, 128, 0, c->stream>>>(c->d_aos, inst0, n, c->d);
+    const uint32_t Np = c->d.N_pad, items = n * dspi::kRoles * DSPI_MAX_BANDS;
+    dspi::chainq_scatter_kernel<<<(items + 255) / 256, 256, 0, c->stream>>>(c->d_aos, inst0, n, Np, (dspi_biquad_q28 *)dspi::eq_aos_mirror(c->eq_m),
+                                                                           (dspi_biquad_q28 *)dspi::eq_aos_mirror(c->eq_o), 1);
     CU_OK(cudaGetLastError());
     c->launches++;
+    for (int role = 0; role < dspi::kRoles; role++) {
+        int rc = role < 2 ? dspi::eq_pack_range(c->eq_m, role * Np + inst0, n, c->stream)
+                          : dspi::eq_pack_range(c->eq_o, (role - 2) * Np + inst0, n, c->stream);
+        if (rc) return rc;
+    }
     CU_OK(cudaStreamSynchronize(c->stream));
     return DSPI_OK;
 }
@@ -724,7 +871,14 @@ int dspi_chainq_download_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, dsp
     if (n == 0) return DSPI_OK;
     CU_OK(cudaSetDevice(c->desc.device));
     const size_t row = (size_t)dspi::kRoles * DSPI_MAX_BANDS;
-    dspi::chainq_unpack_kernel<<<(n * row + 127) / 128, 128, 0, c->stream>>>(c->d_aos, inst0, n, c->d);
+    const uint32_t Np = c->d.N_pad, items = n * dspi::kRoles * DSPI_MAX_BANDS;
+    for (int role = 0; role < dspi::kRoles; role++) {
+        int rc = role < 2 ? dspi::eq_unpack_range(c->eq_m, role * Np + inst0, n, c->stream)
+                          : dspi::eq_unpack_range(c->eq_o, (role - 2) * Np + inst0, n, c->stream);
+        if (rc) return rc;
+    }
+    dspi::chainq_scatter_kernel<<<(items + 255) / 256, 256, 0, c->stream>>>(c->d_aos, inst0, n, Np, (dspi_biquad_q28 *)dspi::eq_aos_mirror(c->eq_m),
+                                                                           (dspi_biquad_q28 *)dspi::eq_aos_mirror(c->eq_o), 0);
     CU_OK(cudaGetLastError());
     c->launches++;
     CU_OK(cudaMemcpyAsync(biquads, c->d_aos + inst0 * row, n * row * sizeof(dspi_biquad_q28), cudaMemcpyDeviceToHost, c->stream));
@@ -742,35 +896,47 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
     if ((uint64_t)n_packets * fpp > c->desc.max_frames) return fail(DSPI_ERANGE, "%u frames exceed max_frames %u", n_packets * fpp, c->desc.max_frames);
     CU_OK(cudaSetDevice(c->desc.device));
     const uint32_t F = n_packets * fpp;
-    const size_t smem = (size_t)4 * dspi::kPkt * 32 * 4;
+    const size_t post_smem = (size_t)4 * 2 * fpp * dspi::kXs * 4;           // 4 warps x (packet + look-ahead columns)
     static bool configured = false;
     if (!configured) {
-        CU_OK(cudaFuncSetAttribute(dspi::chainq_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU_OK(cudaFuncSetAttribute(dspi::chainq_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_OK(cudaFuncSetAttribute(dspi::chainq_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * 2 * dspi::kPkt * dspi::kXs * 4)));
         configured = true;
     }
-    // Stage pipeline over packet slices on three streams (chain_streams.cuh).
+    // Stage pipeline over packet slices on three streams (chain_streams.cuh), stages as in chain_f32.cu.
     dspi::ChainStreams &st = c->st;
     const uint32_t n_slices = n_packets < (uint32_t)dspi::ChainStreams::kMaxSlices ? n_packets : (uint32_t)dspi::ChainStreams::kMaxSlices;
+    const ChainQ d = c->d;
+    const uint32_t n_sms = 148;
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
     CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t p0 = (uint32_t)((uint64_t)n_packets * sl / n_slices), p1 = (uint32_t)((uint64_t)n_packets * (sl + 1) / n_slices);
-        const ChainQ d = c->d;
-        const uint32_t fwarps = d.N_pad / 16, owarps = d.N_pad / 32 * dspi::kOuts;
-        dspi::chainq_front_kernel<<<(fwarps + 3) / 4, 128, smem, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, p0, p1 - p0, fpp, F);
+        const uint32_t fb = p0 * fpp, fe = p1 * fpp;
+        int rc;
+        dspi::chainq_pre_kernel<<<(d.N_pad / 32 + 1) / 2, 64, 0, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, fb, fe, F);
+        CU_OK(cudaGetLastError());
+        if ((rc = dspi::eq_process_on(c->eq_m, d.mrow + fb, fe - fb, d.ldF, st.s_front)) != DSPI_OK) return rc;
+        dspi::chainq_post_kernel<<<(d.N_pad / 16 + 3) / 4, 128, post_smem, st.s_front>>>(d, p0, p1 - p0, fpp);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_front[sl], st.s_front));
         CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
-        dspi::chainq_out_kernel<<<(owarps + 3) / 4, 128, smem, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        dspi::chainq_mix_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, fb, fe);
         CU_OK(cudaGetLastError());
-        std::swap(c->d.widx_in, c->d.widx_out);
+        if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
+        dspi::chainq_outpost_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
         CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
-        dspi::chainq_pdm_kernel<<<(d.N + 63) / 64, 64, 0, st.s_pdm>>>(d, p0 * fpp, p1 * fpp, F, d_pdm);
+        dspi::chainq_pdm_kernel<<<(d.N + 127) / 128, 128, 0, st.s_pdm>>>(d, fb, fe, F, d_pdm);
         CU_OK(cudaGetLastError());
-        c->launches += 3;
+        c->launches += 5;
     }
+    dspi::chainq_ring_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, F);            // after the last outpost launch (stream order)
+    CU_OK(cudaGetLastError());
+    c->launches++;
+    std::swap(c->d.widx_in, c->d.widx_out);
+    CU_OK(cudaEventRecord(st.ev_aux, st.s_out));
+    CU_OK(cudaStreamWaitEvent(c->stream, st.ev_aux, 0));
     CU_OK(cudaEventRecord(st.ev_done, st.s_pdm));
     CU_OK(cudaStreamWaitEvent(c->stream, st.ev_done, 0));
     if (d_status) {
@@ -811,6 +977,9 @@ int dspi_chainq_sync(dspi_chainq *c)
     return DSPI_OK;
 }
 
-uint64_t dspi_chainq_launch_count(dspi_chainq *c) { return c ? c->launches : 0; }
+uint64_t dspi_chainq_launch_count(dspi_chainq *c)
+{
+    return c ? c->launches + dspi_eq_launch_count(c->eq_m) + dspi_eq_launch_count(c->eq_o) : 0;
+}
 
 }  // extern "C"

@@ -381,7 +381,12 @@ void *eq_aos_mirror(dspi_eq *e) { return e->d_aos; }
 
 static int remask(dspi_eq *e, cudaStream_t s)
 {
-    if (!e->d_skip || !e->d_modes) return DSPI_OK;
+    if (!e->d_skip) return DSPI_OK;
+    if (e->desc.arith == DSPI_ARITH_Q28) {
+        CU_OK(launch_skip_q28((int32_t *)e->d_coef, e->d_skip, e->desc.n_channels, s));
+        e->launches++;
+        return DSPI_OK;
+    }
     if (!e->d_modes_eff) {
         CU_OK(cudaMalloc(&e->d_modes_eff, (size_t)e->c_pad * 8));
         CU_OK(cudaMemsetAsync(e->d_modes_eff, 0, (size_t)e->c_pad * 8, s));

@@ -50,5 +50,6 @@ int eq_unpack_range(dspi_eq *e, uint32_t ch0, uint32_t n, cudaStream_t s); // pa
 // device memory owned by the caller; call again after changing it.
 int eq_set_skip(dspi_eq *e, const uint8_t *d_skip, cudaStream_t s);
 int eq_process_on(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStream_t s);
+cudaError_t launch_skip_q28(int32_t *coef, const uint8_t *skip, uint32_t n, cudaStream_t stream);
 cudaError_t launch_mask_modes(const uint64_t *raw, const uint8_t *skip, uint64_t *eff, uint32_t n, cudaStream_t stream);
 }  // namespace dspi

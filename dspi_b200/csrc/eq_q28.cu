@@ -118,6 +118,7 @@ eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ sa
         s2[b] = (uint32_t)cg[(b * kSlots + 16) * 32 + lane];
         if (cg[(b * kSlots + 17) * 32 + lane]) byp |= 1u << b;
     }
+    if (cg[18 * 32 + lane]) byp = (1u << NB) - 1u;              // whole row frozen (chain engines: eq_set_skip)
     uint32_t all_byp = 0, any_byp = 0;
 #pragma unroll
     for (int b = 0; b < NB; b++) {
@@ -259,6 +260,20 @@ __global__ void pack_q28_kernel(const dspi_biquad_q28 *__restrict__ aos, uint32_
         dst[16 * 32] = q.s2;
         dst[17 * 32] = q.bypass ? 1 : 0;
     }
+}
+
+// row skip flags (chain engines): slot 18 of band 0
+__global__ void skip_q28_kernel(int32_t *__restrict__ coef, const uint8_t *__restrict__ skip, uint32_t n)
+{
+    const uint32_t ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n) return;
+    coef[((size_t)(ch / 32) * kMaxBands * kSlots + 18) * 32 + ch % 32] = skip[ch] ? 1 : 0;
+}
+cudaError_t launch_skip_q28(int32_t *coef, const uint8_t *skip, uint32_t n, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    skip_q28_kernel<<<(n + 255) / 256, 256, 0, stream>>>(coef, skip, n);
+    return cudaGetLastError();
 }
 
 __global__ void unpack_q28_kernel(dspi_biquad_q28 *__restrict__ aos, uint32_t ch0, uint32_t n, const int32_t *__restrict__ coef)

@@ -15,7 +15,9 @@ from tests.orc import make_orc_chain, make_orc_chain_q28, orc_chain_run, orc_cha
 
 
 def _instances(platform, n, fs, vol):
-    Ps, bqs = [], []
+    q28 = platform == L.PLATFORM_RP2040
+    Ps = np.zeros(n, L.CHAIN_PARAMS_Q28 if q28 else L.CHAIN_PARAMS_F32)       # (np.concatenate would re-pack the padded C layouts)
+    bqs = np.zeros((n, L.CHAINQ_EQ_CHANNELS if q28 else L.CHAIN_EQ_CHANNELS, L.MAX_BANDS), L.BIQUAD_Q28 if q28 else L.BIQUAD_F32)
     for i in range(n):
         st = api.bulk_state_defaults(platform)
         w = wire_packet(platform, 300 + i)
@@ -25,9 +27,9 @@ def _instances(platform, n, fs, vol):
         w["crosspoints"][0]["enabled"][:] = 1
         assert api.bulk_params_apply(w, st) == 0
         P, bq = api.bulk_state_to_chain(st, fs, vol)
-        Ps.append(P)
-        bqs.append(bq)
-    return np.concatenate(Ps), np.concatenate(bqs)
+        Ps[i] = P[0]
+        bqs[i] = bq[0]
+    return Ps, bqs
 
 
 def test_float_chain_from_wire_packets(oracle):
@@ -43,7 +45,14 @@ def test_float_chain_from_wire_packets(oracle):
         for i in range(N):
             ch = make_orc_chain(oracle, P[i], bq[i])
             ws, wp = orc_chain_run(oracle, "f32f", ch, pcm[i], 24, npk, fpp)
-            assert np.array_equal(spdif[i], ws), f"instance {i}: S/PDIF words differ"
+            if not np.array_equal(spdif[i], ws):
+                bad = np.argwhere(spdif[i] != ws)
+                pair, frame, chn = bad[0]
+                o = 2 * pair + chn
+                raise AssertionError(f"instance {i}: S/PDIF words differ first at pair {pair} frame {frame} ch {chn} ({len(bad)} words, outputs "
+                                     f"{sorted(set((2 * b[0] + b[2]) for b in bad))}); output {o}: {P[i]['matrix']['outputs'][o]} "
+                                     f"xp {P[i]['matrix']['crosspoints'][:, o]} flags bypass={P[i]['bypass_master_eq']} loud={P[i]['loudness_enabled']} "
+                                     f"xf={P[i]['crossfeed_enabled']} lev={P[i]['leveller_enabled']} gpu {spdif[i][pair, frame, chn]} want {ws[pair, frame, chn]}")
             if P[i]["matrix"]["outputs"][8]["enabled"]:
                 assert np.array_equal(pdm[i], wp), f"instance {i}: PDM differs"
             assert list(status[i]["peaks"]) == list(ch.peaks)
