@@ -113,12 +113,6 @@ __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
-// pull one 128-byte line towards this SM's L1 (no register, no fault semantics needed: callers pass valid addresses)
-__device__ __forceinline__ void prefetch_l1(const void *p)
-{
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-}
-
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

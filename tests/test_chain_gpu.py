@@ -85,3 +85,15 @@ def test_chain_without_leveller_is_libm_free(oracle):
                 assert np.array_equal(pdm[i], wp)
     finally:
         eng.close()
+
+
+def test_chain_24bit_odd_frame_count(oracle):
+    """44.1 kHz-like packets: 45 frames x 7 packets = 315 frames of packed 24-bit PCM - instance streams are not
+    word-aligned (byte path of the pre stage) and slices do not start on 16-byte boundaries (K1's non-TMA path)"""
+    _compare(oracle, "f32f", N=35, fs=44100.0, bit_depth=24, n_packets=7, fpp=45, seed=41)
+
+
+def test_chain_call_longer_than_the_delay_ring(oracle):
+    """4608 frames per call > 4096-slot delay rings, two calls: delayed samples come from the output rows inside a call
+    and from the ring across calls; the ring keeps exactly the last 4096 samples"""
+    _compare(oracle, "f32f", N=6, fs=96000.0, bit_depth=16, n_packets=24, fpp=192, seed=51, calls=2)

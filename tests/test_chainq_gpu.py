@@ -59,3 +59,12 @@ def test_chainq_state_carries_across_calls(oracle):
 
 def test_chainq_without_leveller(oracle):
     _compare(oracle, N=32, fs=96000.0, bit_depth=24, n_packets=4, fpp=96, seed=331, leveller=False)
+
+
+def test_chainq_24bit_odd_frame_count(oracle):
+    _compare(oracle, N=35, fs=44100.0, bit_depth=24, n_packets=7, fpp=45, seed=341)
+
+
+def test_chainq_call_longer_than_the_delay_ring(oracle):
+    """2880 frames per call > 2048-slot rings, two calls"""
+    _compare(oracle, N=6, fs=96000.0, bit_depth=16, n_packets=15, fpp=192, seed=351, calls=2)
