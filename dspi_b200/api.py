@@ -32,6 +32,7 @@ SYMBOLS = [
     "dspi_crossfeed_compute_coefficients_q28", "dspi_loudness_compute_table_q28",
     "dspi_spdif_lookup_table", "dspi_spdif_encode_device", "dspi_spdif_encode_host",
     "dspi_bulk_state_defaults", "dspi_bulk_params_apply", "dspi_bulk_params_collect", "dspi_bulk_state_to_chain_f32", "dspi_bulk_state_to_chain_q28",
+    "dspi_preset_slot_size", "dspi_crc32", "dspi_preset_slot_apply", "dspi_preset_slot_collect",
 ]
 
 
@@ -363,6 +364,32 @@ def bulk_state_to_chain(state, fs, host_volume_8_8=0, host_mute=False, biquads=N
     _check(fn(state.ctypes.data_as(C.c_void_p), C.c_float(fs), C.c_int16(int(host_volume_8_8)), int(bool(host_mute)),
               P.ctypes.data_as(C.c_void_p), bq.ctypes.data_as(C.c_void_p)))
     return P, bq
+
+
+def preset_slot_size(platform=L.PLATFORM_RP2350):
+    lib().dspi_preset_slot_size.restype = C.c_size_t
+    return int(lib().dspi_preset_slot_size(int(platform)))
+
+
+def crc32(data):
+    lib().dspi_crc32.restype = C.c_uint32
+    b = bytes(data)
+    return int(lib().dspi_crc32(b, C.c_size_t(len(b))))
+
+
+def preset_slot_collect(state, slot_index):
+    """``collect_live_state`` (flash_storage.c:464-556): the slot image as bytes."""
+    n = preset_slot_size(int(state["platform"][0]))
+    out = np.zeros(n, np.uint8)
+    _check(lib().dspi_preset_slot_collect(state.ctypes.data_as(C.c_void_p), int(slot_index), out.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+    return out
+
+
+def preset_slot_apply(image, slot_index, state, master_volume_mode=0, dir_master_volume_db=0.0):
+    """The state part of ``preset_load`` on ``state`` (in place).  Returns 0 or 3 (PRESET_ERR_CRC)."""
+    img = np.ascontiguousarray(image, np.uint8)
+    return int(lib().dspi_preset_slot_apply(img.ctypes.data_as(C.c_void_p), C.c_size_t(img.size), int(slot_index), int(master_volume_mode),
+                                           C.c_float(dir_master_volume_db), state.ctypes.data_as(C.c_void_p)))
 
 
 SPDIF_CHANNEL_STATUS = bytes([0x04, 0x00, 0x00, 0x00, 0x0B])       # audio_spdif.c:82-88 (byte 3 = sample-rate code, set at run time)

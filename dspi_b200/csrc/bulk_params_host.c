@@ -312,3 +312,176 @@ int dspi_bulk_state_to_chain_q28(const dspi_bulk_state *st, float fs, int16_t ho
         }
     return DSPI_OK;
 }
+
+/* ================================================================================================
+ * Preset slot images — flash_storage.c (PresetSlot v12 :139-189, crc32 :282-291, db_to_linear :302-306,
+ * collect_live_state :464-556, apply_master_volume_db :558-571, apply_master_volume_from_mode :580-590,
+ * apply_slot_to_live :597-744, validate_slot :750-760)
+ * ================================================================================================ */
+uint32_t dspi_crc32(const void *data, size_t len)
+{
+    const uint8_t *p = (const uint8_t *)data;
+    uint32_t crc = 0xFFFFFFFFu;
+    for (size_t i = 0; i < len; i++) {
+        crc ^= p[i];
+        for (int j = 0; j < 8; j++) crc = (crc >> 1) ^ (0xEDB88320u & (0u - (crc & 1u)));
+    }
+    return ~crc;
+}
+
+/* flash_storage.c:302-306 */
+static float db_to_linear_flash(float db)
+{
+    if (db <= -120.0f) return 0.0f;
+    if (db >= 80.0f) db = 80.0f;
+    return powf(10.0f, db / 20.0f);
+}
+
+#define SLOT_STRUCT(NAME, NC, NO, NPIN)                                                                              \
+    typedef struct __attribute__((packed)) {                                                                         \
+        uint32_t magic; uint16_t version, slot_index; uint32_t crc32;                                                \
+        dspi_eq_param filter_recipes[NC][DSPI_MAX_BANDS];                                                            \
+        float preamp_db; uint8_t bypass, padding[3];                                                                 \
+        float delays_ms[NC];                                                                                         \
+        float channel_gain_db[3]; uint8_t channel_mute[3], padding2;                                                 \
+        uint8_t loudness_enabled, padding3[3]; float loudness_ref_spl, loudness_intensity_pct;                       \
+        uint8_t crossfeed_enabled, crossfeed_preset, crossfeed_itd_enabled, padding4; float crossfeed_custom_fc, crossfeed_custom_feed_db; \
+        struct __attribute__((packed)) { uint8_t enabled, phase_invert, reserved[2]; float gain_db; } matrix_crosspoints[2][NO]; \
+        struct __attribute__((packed)) { uint8_t enabled, mute, reserved[2]; float gain_db, delay_ms; } matrix_outputs[NO]; \
+        uint8_t output_pins[NPIN], pin_padding[8 - NPIN];                                                            \
+        char channel_names[NC][32];                                                                                  \
+        uint8_t output_types[4], i2s_bck_pin, i2s_mck_pin, i2s_mck_enabled, i2s_mck_multiplier;                      \
+        uint8_t leveller_enabled, leveller_speed, leveller_lookahead, leveller_padding;                              \
+        float leveller_amount, leveller_max_gain_db, leveller_gate_threshold_db;                                     \
+        float preamp_db_per_ch[2]; float master_volume_db;                                                           \
+    } NAME
+
+SLOT_STRUCT(slot_rp2350, 11, 9, 5);
+SLOT_STRUCT(slot_rp2040, 7, 5, 3);
+
+size_t dspi_preset_slot_size(int platform) { return platform == DSPI_PLATFORM_RP2350 ? sizeof(slot_rp2350) : sizeof(slot_rp2040); }
+
+/* flash_storage.c:558-571 */
+static void apply_master_volume_db(dspi_bulk_state *st, float db)
+{
+    if (!isfinite(db)) db = 0.0f;
+    if (db < -128.0f) db = -128.0f;
+    if (db > 0.0f) db = 0.0f;
+    st->master_volume_db = db;
+    if (db <= -128.0f) { st->master_volume_linear = 0.0f; st->master_volume_q15 = 0; }
+    else {
+        const float lin = powf(10.0f, db / 20.0f);
+        st->master_volume_linear = lin;
+        st->master_volume_q15 = f2i_sat(lin * 32768.0f);
+    }
+}
+
+#define SLOT_IMPL(SUF, TYPE, NC, NO)                                                                                 \
+    static int apply_##SUF(const TYPE *s, uint8_t slot_index, uint8_t mv_mode, float dir_mv_db, dspi_bulk_state *st) \
+    {                                                                                                                \
+        if (s->magic != DSPI_PRESET_SLOT_MAGIC) return DSPI_PRESET_ERR_CRC;                         /* :752 */        \
+        if (s->slot_index != slot_index) return DSPI_PRESET_ERR_CRC;                                /* :753 */        \
+        if (dspi_crc32(&s->filter_recipes, sizeof(TYPE) - offsetof(TYPE, filter_recipes)) != s->crc32) return DSPI_PRESET_ERR_CRC;   /* :755-757 */ \
+        memcpy(st->recipes, s->filter_recipes, sizeof(s->filter_recipes));                          /* :599 */        \
+        for (int i = 0; i < 2; i++) {                                                               /* :602-617 */    \
+            const float db = s->version >= 12 ? s->preamp_db_per_ch[i] : s->preamp_db, lin = db_to_linear_flash(db);  \
+            st->preamp_db[i] = db; st->preamp_q28[i] = f2i_sat(lin * (float)(1 << 28)); st->preamp_linear[i] = lin;   \
+        }                                                                                                            \
+        st->bypass_master_eq = s->bypass != 0;                                                      /* :620 */        \
+        memcpy(st->channel_delays_ms, s->delays_ms, sizeof(s->delays_ms));                          /* :623 */        \
+        for (int i = 0; i < 3; i++) {                                                               /* :626-631 */    \
+            st->legacy_gain_db[i] = s->channel_gain_db[i];                                                           \
+            st->legacy_gain_mul[i] = f2i_sat(db_to_linear_flash(s->channel_gain_db[i]) * 32768.0f);                  \
+            st->legacy_mute[i] = s->channel_mute[i] != 0;                                                            \
+        }                                                                                                            \
+        st->loudness_enabled = s->loudness_enabled != 0;                                            /* :634-637 */    \
+        st->loudness_ref_spl = s->loudness_ref_spl;                                                                  \
+        st->loudness_intensity_pct = s->loudness_intensity_pct;                                                      \
+        st->crossfeed.enabled = s->crossfeed_enabled != 0;                                          /* :640-645 */    \
+        st->crossfeed.preset = s->crossfeed_preset;                                                                  \
+        st->crossfeed.itd_enabled = s->crossfeed_itd_enabled != 0;                                                   \
+        st->crossfeed.custom_fc = s->crossfeed_custom_fc;                                                            \
+        st->crossfeed.custom_feed_db = s->crossfeed_custom_feed_db;                                                  \
+        for (int in = 0; in < 2; in++)                                                              /* :648-655 */    \
+            for (int o = 0; o < NO; o++) {                                                                           \
+                dspi_matrix_crosspoint *x = &st->crosspoints[in][o];                                                 \
+                x->enabled = s->matrix_crosspoints[in][o].enabled;                                                   \
+                x->phase_invert = s->matrix_crosspoints[in][o].phase_invert;                                         \
+                x->gain_db = s->matrix_crosspoints[in][o].gain_db;                                                   \
+                x->gain_linear = db_to_linear_flash(s->matrix_crosspoints[in][o].gain_db);                           \
+            }                                                                                                        \
+        for (int o = 0; o < NO; o++) {                                                              /* :656-663 */    \
+            dspi_output_channel *oc = &st->outputs[o];                                                               \
+            oc->enabled = s->matrix_outputs[o].enabled;                                                              \
+            oc->mute = s->matrix_outputs[o].mute;                                                                    \
+            oc->gain_db = s->matrix_outputs[o].gain_db;                                                              \
+            oc->gain_linear = db_to_linear_flash(s->matrix_outputs[o].gain_db);                                      \
+            oc->delay_ms = s->matrix_outputs[o].delay_ms;                                                            \
+            st->channel_delays_ms[CH_OUT_1 + o] = s->matrix_outputs[o].delay_ms;                                     \
+        }                                                                                                            \
+        if (s->version >= 10) {                                                                     /* :724-741 */    \
+            st->leveller.enabled = s->leveller_enabled != 0;                                                         \
+            st->leveller.speed = s->leveller_speed;                                                                  \
+            st->leveller.lookahead = s->leveller_lookahead != 0;                                                     \
+            st->leveller.amount = s->leveller_amount;                                                                \
+            st->leveller.max_gain_db = s->leveller_max_gain_db;                                                      \
+            st->leveller.gate_threshold_db = s->leveller_gate_threshold_db;                                          \
+        } else {                                                                                                     \
+            st->leveller.enabled = 0; st->leveller.amount = 50.0f; st->leveller.speed = 0;                           \
+            st->leveller.max_gain_db = 15.0f; st->leveller.lookahead = 1; st->leveller.gate_threshold_db = -96.0f;   \
+        }                                                                                                            \
+        apply_master_volume_db(st, (mv_mode == 1 && s->version >= 12) ? s->master_volume_db : dir_mv_db);   /* :580-590 */ \
+        return DSPI_PRESET_OK;                                                                                       \
+    }                                                                                                                \
+    static void collect_##SUF(const dspi_bulk_state *st, uint8_t slot_index, TYPE *s)                                \
+    {                                                                                                                \
+        memset(s, 0, sizeof(*s));                                                                                    \
+        s->magic = DSPI_PRESET_SLOT_MAGIC; s->version = DSPI_PRESET_SLOT_VERSION; s->slot_index = slot_index;        \
+        memcpy(s->filter_recipes, st->recipes, sizeof(s->filter_recipes));                                           \
+        s->preamp_db = st->preamp_db[0];                                                                             \
+        s->bypass = st->bypass_master_eq ? 1 : 0;                                                                    \
+        memcpy(s->delays_ms, st->channel_delays_ms, sizeof(s->delays_ms));                                           \
+        for (int i = 0; i < 3; i++) { s->channel_gain_db[i] = st->legacy_gain_db[i]; s->channel_mute[i] = st->legacy_mute[i] ? 1 : 0; } \
+        s->loudness_enabled = st->loudness_enabled ? 1 : 0;                                                          \
+        s->loudness_ref_spl = st->loudness_ref_spl; s->loudness_intensity_pct = st->loudness_intensity_pct;          \
+        s->crossfeed_enabled = st->crossfeed.enabled ? 1 : 0; s->crossfeed_preset = st->crossfeed.preset;            \
+        s->crossfeed_itd_enabled = st->crossfeed.itd_enabled ? 1 : 0;                                                \
+        s->crossfeed_custom_fc = st->crossfeed.custom_fc; s->crossfeed_custom_feed_db = st->crossfeed.custom_feed_db; \
+        for (int in = 0; in < 2; in++)                                                                               \
+            for (int o = 0; o < NO; o++) {                                                                           \
+                s->matrix_crosspoints[in][o].enabled = st->crosspoints[in][o].enabled;                               \
+                s->matrix_crosspoints[in][o].phase_invert = st->crosspoints[in][o].phase_invert;                     \
+                s->matrix_crosspoints[in][o].gain_db = st->crosspoints[in][o].gain_db;                               \
+            }                                                                                                        \
+        for (int o = 0; o < NO; o++) {                                                                               \
+            s->matrix_outputs[o].enabled = st->outputs[o].enabled; s->matrix_outputs[o].mute = st->outputs[o].mute;  \
+            s->matrix_outputs[o].gain_db = st->outputs[o].gain_db; s->matrix_outputs[o].delay_ms = st->outputs[o].delay_ms; \
+        }                                                                                                            \
+        s->leveller_enabled = st->leveller.enabled ? 1 : 0; s->leveller_speed = st->leveller.speed;                  \
+        s->leveller_lookahead = st->leveller.lookahead ? 1 : 0; s->leveller_amount = st->leveller.amount;            \
+        s->leveller_max_gain_db = st->leveller.max_gain_db; s->leveller_gate_threshold_db = st->leveller.gate_threshold_db; \
+        for (int i = 0; i < 2; i++) s->preamp_db_per_ch[i] = st->preamp_db[i];                                       \
+        s->master_volume_db = st->master_volume_db;                                                                  \
+        s->crc32 = dspi_crc32(&s->filter_recipes, sizeof(TYPE) - offsetof(TYPE, filter_recipes));                    \
+    }
+
+SLOT_IMPL(rp2350, slot_rp2350, 11, 9)
+SLOT_IMPL(rp2040, slot_rp2040, 7, 5)
+
+int dspi_preset_slot_apply(const void *slot, size_t len, uint8_t slot_index, uint8_t master_volume_mode, float dir_master_volume_db,
+                           dspi_bulk_state *st)
+{
+    if (!slot || !st) return DSPI_EINVAL;
+    if (len < dspi_preset_slot_size(st->platform)) return DSPI_PRESET_ERR_CRC;
+    if (st->platform == DSPI_PLATFORM_RP2350) return apply_rp2350((const slot_rp2350 *)slot, slot_index, master_volume_mode, dir_master_volume_db, st);
+    return apply_rp2040((const slot_rp2040 *)slot, slot_index, master_volume_mode, dir_master_volume_db, st);
+}
+
+int dspi_preset_slot_collect(const dspi_bulk_state *st, uint8_t slot_index, void *out, size_t cap)
+{
+    if (!st || !out) return DSPI_EINVAL;
+    if (cap < dspi_preset_slot_size(st->platform)) return DSPI_ERANGE;
+    if (st->platform == DSPI_PLATFORM_RP2350) collect_rp2350(st, slot_index, (slot_rp2350 *)out);
+    else collect_rp2040(st, slot_index, (slot_rp2040 *)out);
+    return DSPI_OK;
+}

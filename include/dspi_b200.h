@@ -384,6 +384,26 @@ int dspi_bulk_state_to_chain_f32(const dspi_bulk_state *st, float sample_rate, i
 int dspi_bulk_state_to_chain_q28(const dspi_bulk_state *st, float sample_rate, int16_t host_volume_8_8, int host_mute,
                                  dspi_chain_params_q28 *params, dspi_biquad_q28 biquads[7][DSPI_MAX_BANDS]);
 
+/* ---- preset slot images: PresetSlot v12, flash_storage.c:139-189 ------------ */
+/* One flash sector per slot: 12-byte header (magic "DSP3", data version, slot index, CRC-32 of everything
+ * after the header) + the packed DSP state.  Device preset dumps load directly into a dspi_bulk_state and
+ * from there (dspi_bulk_state_to_chain_*) into a chain engine. */
+#define DSPI_PRESET_SLOT_MAGIC   0x44535033u     /* flash_storage.c:67 */
+#define DSPI_PRESET_SLOT_VERSION 12              /* :71 */
+#define DSPI_PRESET_OK       0                   /* config.h:262-266 */
+#define DSPI_PRESET_ERR_CRC  3
+size_t dspi_preset_slot_size(int platform);                       /* sizeof(PresetSlot) on that platform */
+uint32_t dspi_crc32(const void *data, size_t len);               /* flash_storage.c:282-291 (reflected 0xEDB88320) */
+/* validate_slot() (:750-760) + apply_slot_to_live() (:597-744) + apply_master_volume_from_mode() (:580-590),
+ * i.e. the state part of preset_load(): DSPI_PRESET_OK, or DSPI_PRESET_ERR_CRC when magic, slot index or CRC
+ * do not match (state untouched).  Gains use flash_storage.c's db_to_linear (powf, :302-306), not the Taylor
+ * series of the bulk path.  master_volume_mode / dir_master_volume_db are the directory's settings
+ * (MASTER_VOLUME_MODE_INDEPENDENT = 0: use dir_master_volume_db; 1: the slot's own value when version >= 12). */
+int dspi_preset_slot_apply(const void *slot, size_t len, uint8_t slot_index, uint8_t master_volume_mode, float dir_master_volume_db,
+                           dspi_bulk_state *st);
+/* collect_live_state() (:464-556): writes dspi_preset_slot_size(st->platform) bytes (pins, names, I2S: zero) */
+int dspi_preset_slot_collect(const dspi_bulk_state *st, uint8_t slot_index, void *out, size_t cap);
+
 /* ---- S/PDIF (IEC 60958) subframe encoder: the step after the chain -------------------------- */
 /* What stereo_to_spdif_producer_give_s32() does with every S/PDIF producer buffer
  * (pico_audio_spdif_multi/sample_encoding.cpp:42-50 -> spdif_update_subframe,

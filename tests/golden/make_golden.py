@@ -149,9 +149,43 @@ def make_bulk():
     print("bulk.npz", os.path.getsize(os.path.join(HERE, "bulk.npz")), "bytes")
 
 
+def make_preset():
+    """Fixture E "preset": device states, the slot images the reference's preset_save() writes for them, and the states
+    its preset_load() leaves when those images are loaded into a factory-default device (both platforms)."""
+    import ctypes as C
+    from dspi_b200 import api
+    from tests.bulk_cases import wire_packet
+    from tests.orc import ORACLE_DIR
+    save = {}
+    for platform, key in ((L.PLATFORM_RP2350, "rp2350"), (L.PLATFORM_RP2040, "rp2040")):
+        ref = C.CDLL(os.path.join(ORACLE_DIR, "_ref", f"libdspi_ref_preset_{key}.so"))
+        ref.ref_preset_load.argtypes = [C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint8, C.c_float, C.c_void_p]
+        n = api.preset_slot_size(platform)
+        states, images, loaded, slots = [], [], [], []
+        for i in range(4):
+            st = api.bulk_state_defaults(platform)
+            assert api.bulk_params_apply(wire_packet(platform, 900 + i), st, exact_db=True) == 0
+            sector = np.zeros(4096, np.uint8)
+            assert ref.ref_preset_save(st.ctypes.data_as(C.c_void_p), i + 3, sector.ctypes.data_as(C.c_void_p)) == 0
+            out = api.bulk_state_defaults(platform)
+            assert ref.ref_preset_load(sector.ctypes.data, n, i + 3, 1, 0.0, out.ctypes.data) == 0
+            over = out["preamp_linear"] * np.float32(2.0 ** 28) >= np.float32(2.0 ** 31)          # ARM saturation (SURVEY quirk 7)
+            out["preamp_q28"][over & (out["preamp_q28"] == np.iinfo(np.int32).min)] = np.iinfo(np.int32).max
+            states.append(st.copy()); images.append(sector[:n].copy()); loaded.append(out.copy()); slots.append(i + 3)
+        save[f"{key}_state"] = np.frombuffer(b"".join(x.tobytes() for x in states), np.uint8).reshape(len(states), -1)
+        save[f"{key}_loaded"] = np.frombuffer(b"".join(x.tobytes() for x in loaded), np.uint8).reshape(len(loaded), -1)
+        save[f"{key}_image"] = np.stack(images)
+        save[f"{key}_slot"] = np.array(slots, np.int32)
+    np.savez_compressed(os.path.join(HERE, "preset.npz"), **save)
+    print("preset.npz", os.path.getsize(os.path.join(HERE, "preset.npz")), "bytes")
+
+
 if __name__ == "__main__":
     if "--bulk" in sys.argv:
         make_bulk()
+    elif "--preset" in sys.argv:
+        make_preset()
     else:
         main()
         make_bulk()
+        make_preset()
