@@ -21,7 +21,7 @@ SYMBOLS = [
     "dspi_last_error", "dspi_device_count", "dspi_compute_coefficients_f32", "dspi_compute_coefficients_q28",
     "dspi_eq_create", "dspi_eq_destroy", "dspi_eq_upload_biquads", "dspi_eq_download_biquads", "dspi_eq_set_param",
     "dspi_eq_process_device", "dspi_eq_process_host", "dspi_eq_sync", "dspi_eq_stream", "dspi_eq_launch_count",
-    "dspi_eq_kernel_info",
+    "dspi_eq_kernel_info", "dspi_eq_set_params_device",
     "dspi_host_alloc", "dspi_host_free",
     "dspi_chain_create", "dspi_chain_destroy", "dspi_chain_set_params", "dspi_chain_upload_biquads", "dspi_chain_download_biquads",
     "dspi_chain_reset_state", "dspi_chain_process_host", "dspi_chain_process_device", "dspi_chain_sync", "dspi_chain_stream",
@@ -220,6 +220,13 @@ class EqEngine:
     @property
     def launch_count(self):
         return int(lib().dspi_eq_launch_count(self._h))
+
+    def set_params_device(self, recipes, fs, ch0=0):
+        """``dsp_compute_coefficients`` for every band of ``recipes`` (EQ_PARAM [n, 12]) on the GPU; returns the clamped recipes."""
+        r = np.ascontiguousarray(recipes, L.EQ_PARAM).copy()
+        assert r.ndim == 2 and r.shape[1] == L.MAX_BANDS
+        _check(lib().dspi_eq_set_params_device(self._h, int(ch0), int(r.shape[0]), r.ctypes.data_as(C.c_void_p), C.c_float(fs)))
+        return r
 
     def kernel_info(self):
         """Which kernel the next process call runs (triggers a pending run-time specialisation)."""

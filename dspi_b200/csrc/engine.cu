@@ -244,6 +244,25 @@ int dspi_eq_download_biquads(dspi_eq *e, uint32_t ch0, uint32_t n, void *biquads
     return DSPI_OK;
 }
 
+int dspi_eq_set_params_device(dspi_eq *e, uint32_t ch0, uint32_t n, dspi_eq_param *recipes, float sample_rate)
+{
+    int rc = check_range(e, ch0, n, recipes);
+    if (rc) return rc;
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(e->desc.device));
+    const size_t bytes = (size_t)n * DSPI_MAX_BANDS * sizeof(dspi_eq_param);
+    dspi_eq_param *d_rec = nullptr;
+    CU_OK(cudaMalloc((void **)&d_rec, bytes));
+    cudaError_t err = cudaMemcpyAsync(d_rec, recipes, bytes, cudaMemcpyHostToDevice, e->stream);
+    if (err == cudaSuccess) err = dspi::launch_coeffs(e->desc.arith == DSPI_ARITH_Q28, d_rec, e->d_aos, ch0, n, sample_rate, e->stream);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(recipes, d_rec, bytes, cudaMemcpyDeviceToHost, e->stream);   // the clamps, like the reference's write-back
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(d_rec);
+    if (err != cudaSuccess) return fail(DSPI_ECUDA, "coefficient generation: %s", cudaGetErrorString(err));
+    e->launches++;
+    return dspi::eq_pack_range(e, ch0, n, e->stream);          // mirror -> packed store (and topology words)
+}
+
 int dspi_eq_set_param(dspi_eq *e, uint32_t channel, dspi_eq_param *p, float sample_rate)
 {
     if (!e || !p) return fail(DSPI_EINVAL, "null argument");

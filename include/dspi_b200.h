@@ -127,6 +127,14 @@ int dspi_eq_download_biquads(dspi_eq *e, uint32_t ch0, uint32_t n, void *biquads
  * band of one channel from its recipe and upload it.  p->channel is ignored
  * (8 bits on the wire); `channel` selects the row, p->band the band. */
 int dspi_eq_set_param(dspi_eq *e, uint32_t channel, dspi_eq_param *p, float sample_rate);
+/* Mass reconfiguration (device part): dsp_compute_coefficients() for all 12 bands of channels
+ * [ch0, ch0 + n) ON THE GPU, straight into the engine's stores - recipes[n][DSPI_MAX_BANDS] (host memory) are
+ * clamped in place like the reference does (dsp_pipeline.c:78-81); filter state is kept unless a band's
+ * topology flips (:87-92).  Arithmetic is the reference's float arithmetic operation by operation; its libm
+ * calls (powf, tanf, sinf, cosf) are evaluated in double and rounded once ("libm policy"), which
+ * can differ from a host libm's float functions in a last bit - use dspi_compute_coefficients_* +
+ * dspi_eq_upload_biquads when coefficients must be those of a particular host libm. */
+int dspi_eq_set_params_device(dspi_eq *e, uint32_t ch0, uint32_t n, dspi_eq_param *recipes, float sample_rate);
 
 /* Process T samples of every channel, in place.
  *   *_device: samples is a DEVICE pointer, channel-major [n_channels][ld]

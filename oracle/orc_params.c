@@ -25,7 +25,7 @@ static int eq_is_flat(const orc_eq_param *p)
 static void rbj(const orc_eq_param *p, float A, float fs, float *b, float *a)
 {
     float omega = 2.0f * ORC_PI * p->freq / fs;
-    float sn = sinf(omega), cs = cosf(omega);
+    float sn = orc_sinf(omega), cs = orc_cosf(omega);
     float alpha = sn / (2.0f * p->Q);
     float a0 = 1.0f, a1 = 0.0f, a2 = 0.0f, b0 = 1.0f, b1 = 0.0f, b2 = 0.0f;
     switch (p->type) {
@@ -75,13 +75,13 @@ void orc_eq_coeffs_f32(orc_eq_param *p, orc_biquad_f32 *bq, float fs)
     }
     bq->bypass = 0;
     eq_clamp(p, fs);
-    float A = powf(10.0f, p->gain_db / 40.0f);                           /* :83 */
+    float A = orc_powf(10.0f, p->gain_db / 40.0f);                           /* :83 */
     uint8_t was_svf = bq->use_svf;                                       /* :87-92 */
     bq->use_svf = (p->freq < (fs / 7.5f));
     if (was_svf != bq->use_svf) { bq->s1 = bq->s2 = 0.0f; bq->svic1eq = bq->svic2eq = 0.0f; }
 
     if (bq->use_svf) {                                                   /* :94-138 */
-        float g = tanf(ORC_PI * p->freq / fs);
+        float g = orc_tanf(ORC_PI * p->freq / fs);
         float k = 1.0f / p->Q;
         switch (p->type) {
         case ORC_PEAKING:   k = 1.0f / (p->Q * A); break;
@@ -126,7 +126,7 @@ void orc_eq_coeffs_q28(orc_eq_param *p, orc_biquad_q28 *bq, float fs)
     }
     bq->bypass = 0;
     eq_clamp(p, fs);
-    float A = powf(10.0f, p->gain_db / 40.0f);
+    float A = orc_powf(10.0f, p->gain_db / 40.0f);
     float b[3], a[3];
     rbj(p, A, fs, b, a);
     float scale = (float)(1LL << 28);
