@@ -21,7 +21,7 @@ SYMBOLS = [
     "dspi_last_error", "dspi_device_count", "dspi_compute_coefficients_f32", "dspi_compute_coefficients_q28",
     "dspi_eq_create", "dspi_eq_destroy", "dspi_eq_upload_biquads", "dspi_eq_download_biquads", "dspi_eq_set_param",
     "dspi_eq_process_device", "dspi_eq_process_host", "dspi_eq_sync", "dspi_eq_stream", "dspi_eq_launch_count",
-    "dspi_eq_kernel_info", "dspi_eq_set_params_device",
+    "dspi_eq_kernel_info", "dspi_eq_set_params_device", "dspi_chain_set_eq_params_device", "dspi_chainq_set_eq_params_device",
     "dspi_host_alloc", "dspi_host_free",
     "dspi_chain_create", "dspi_chain_destroy", "dspi_chain_set_params", "dspi_chain_upload_biquads", "dspi_chain_download_biquads",
     "dspi_chain_reset_state", "dspi_chain_process_host", "dspi_chain_process_device", "dspi_chain_sync", "dspi_chain_stream",
@@ -266,6 +266,13 @@ class ChainEngine:
         assert b.dtype == L.BIQUAD_F32 and b.shape[1:] == (L.CHAIN_EQ_CHANNELS, L.MAX_BANDS)
         _check(lib().dspi_chain_upload_biquads(self._h, inst0, b.shape[0], b.ctypes.data))
 
+    def set_eq_params_device(self, recipes, fs, inst0=0):
+        """EQ_PARAM [n, 11, 12] -> coefficients of all bands computed on the GPU; returns the clamped recipes."""
+        r = np.ascontiguousarray(recipes, L.EQ_PARAM).copy()
+        assert r.shape[1:] == (L.CHAIN_EQ_CHANNELS, L.MAX_BANDS)
+        _check(lib().dspi_chain_set_eq_params_device(self._h, int(inst0), int(r.shape[0]), r.ctypes.data_as(C.c_void_p), C.c_float(fs)))
+        return r
+
     def download_biquads(self, n=None, inst0=0):
         n = self.n_instances - inst0 if n is None else n
         out = np.zeros((n, L.CHAIN_EQ_CHANNELS, L.MAX_BANDS), L.BIQUAD_F32)
@@ -463,6 +470,12 @@ class ChainEngineQ28:
         b = np.ascontiguousarray(biquads)
         assert b.dtype == L.BIQUAD_Q28 and b.shape[1:] == (L.CHAINQ_EQ_CHANNELS, L.MAX_BANDS)
         _check(lib().dspi_chainq_upload_biquads(self._h, inst0, b.shape[0], b.ctypes.data))
+
+    def set_eq_params_device(self, recipes, fs, inst0=0):
+        r = np.ascontiguousarray(recipes, L.EQ_PARAM).copy()
+        assert r.shape[1:] == (L.CHAINQ_EQ_CHANNELS, L.MAX_BANDS)
+        _check(lib().dspi_chainq_set_eq_params_device(self._h, int(inst0), int(r.shape[0]), r.ctypes.data_as(C.c_void_p), C.c_float(fs)))
+        return r
 
     def download_biquads(self, n=None, inst0=0):
         n = self.n_instances - inst0 if n is None else n

@@ -864,6 +864,25 @@ int dspi_chainq_upload_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, const
     return DSPI_OK;
 }
 
+int dspi_chainq_set_eq_params_device(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_eq_param *recipes, float sample_rate)
+{
+    if (!c || !recipes) return fail(DSPI_EINVAL, "null argument");
+    if ((uint64_t)inst0 + n > c->desc.n_instances) return fail(DSPI_ERANGE, "instances [%u, %u) outside engine of %u", inst0, inst0 + n, c->desc.n_instances);
+    if (n == 0) return DSPI_OK;
+    const uint32_t Np = c->d.N_pad;
+    std::vector<dspi_eq_param> tmp((size_t)n * DSPI_MAX_BANDS);
+    for (int role = 0; role < dspi::kRoles; role++) {               // filter_recipes[role][band] of every instance -> one engine range per role
+        for (uint32_t i = 0; i < n; i++)
+            memcpy(&tmp[(size_t)i * DSPI_MAX_BANDS], &recipes[((size_t)i * dspi::kRoles + role) * DSPI_MAX_BANDS], DSPI_MAX_BANDS * sizeof(dspi_eq_param));
+        int rc = role < 2 ? dspi_eq_set_params_device(c->eq_m, role * Np + inst0, n, tmp.data(), sample_rate)
+                          : dspi_eq_set_params_device(c->eq_o, (role - 2) * Np + inst0, n, tmp.data(), sample_rate);
+        if (rc) return rc;
+        for (uint32_t i = 0; i < n; i++)                            // the clamps, written back like the reference does
+            memcpy(&recipes[((size_t)i * dspi::kRoles + role) * DSPI_MAX_BANDS], &tmp[(size_t)i * DSPI_MAX_BANDS], DSPI_MAX_BANDS * sizeof(dspi_eq_param));
+    }
+    return DSPI_OK;
+}
+
 int dspi_chainq_download_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_biquad_q28 *biquads)
 {
     if (!c || !biquads) return fail(DSPI_EINVAL, "null argument");

@@ -251,6 +251,10 @@ int dspi_eq_set_params_device(dspi_eq *e, uint32_t ch0, uint32_t n, dspi_eq_para
     if (n == 0) return DSPI_OK;
     CU_OK(cudaSetDevice(e->desc.device));
     const size_t bytes = (size_t)n * DSPI_MAX_BANDS * sizeof(dspi_eq_param);
+    // the mirror must carry the CURRENT filter state before it is edited: dsp_compute_coefficients keeps state
+    // unless the topology flips, and the pack kernel below writes the mirror's state back into the packed store
+    rc = dspi::eq_unpack_range(e, ch0, n, e->stream);
+    if (rc) return rc;
     dspi_eq_param *d_rec = nullptr;
     CU_OK(cudaMalloc((void **)&d_rec, bytes));
     cudaError_t err = cudaMemcpyAsync(d_rec, recipes, bytes, cudaMemcpyHostToDevice, e->stream);

@@ -245,6 +245,9 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
 /* filters[NUM_CHANNELS][MAX_BANDS] of n instances: biquads[n][11][12] (master L, R, Out1..9) */
 int dspi_chain_upload_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_biquad_f32 *biquads);
 int dspi_chain_download_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, dspi_biquad_f32 *biquads);
+/* dsp_recalculate_all_filters() for n instances on the GPU: recipes[n][11][DSPI_MAX_BANDS] = filter_recipes[][] of each
+ * instance (host memory, clamped in place); see dspi_eq_set_params_device for the arithmetic and the libm policy */
+int dspi_chain_set_eq_params_device(dspi_chain *c, uint32_t inst0, uint32_t n, dspi_eq_param *recipes, float sample_rate);
 /* pipeline reset: clears leveller, loudness, delay-line and PDM state (leveller_reset_state(),
  * pdm_processing_loop() restart path); filter state is part of the biquads */
 int dspi_chain_reset_state(dspi_chain *c);
@@ -314,6 +317,7 @@ int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dsp
 /* filters[7][12] per instance: biquads[n][7][12] (master L, R, Out1..4, sub) */
 int dspi_chainq_upload_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, const dspi_biquad_q28 *biquads);
 int dspi_chainq_download_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_biquad_q28 *biquads);
+int dspi_chainq_set_eq_params_device(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_eq_param *recipes, float sample_rate);   /* recipes[n][7][12] */
 int dspi_chainq_reset_state(dspi_chainq *c);
 /* pcm as for dspi_chain_process_host; spdif_out [n_instances][2][n_frames][2]; pdm_out [n_instances][n_frames][8] */
 int dspi_chainq_process_host(dspi_chainq *c, const void *pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t frames_per_packet,

@@ -83,10 +83,18 @@ def test_state_survives_unless_the_topology_flips(oracle):
         x = torch.from_numpy(W.inputs_f32(n, T)).cuda()
         eng.process_device(x.data_ptr(), T, T)
         eng.sync()
-        before = eng.download()
         rec2 = rec.copy()
         rec2["gain_db"][:, 1] += 1.0                      # same topology: state kept
         rec2["freq"][:, 2] = 15000.0                      # SVF -> TDF2 at 96 kHz (>= fs / 7.5): state cleared
+        # a twin engine provides the state "before" so that the engine under test is reconfigured with nothing but
+        # its live, packed state (no download in between)
+        twin = api.EqEngine("f32f", n, 10)
+        twin.set_params_device(rec, fs)
+        y = torch.from_numpy(W.inputs_f32(n, T)).cuda()
+        twin.process_device(y.data_ptr(), T, T)
+        twin.sync()
+        before = twin.download()
+        twin.close()
         eng.set_params_device(rec2, fs)
         after = eng.download()
     finally:
@@ -118,3 +126,28 @@ def test_mass_reconfiguration_throughput():
         eng.close()
     print(f"\n8.65 M coefficient sets (recipes H2D, kernel, clamps D2H, pack): {dt * 1e3:.1f} ms = {n * 12 / dt / 1e6:.0f} M sets/s")
     assert dt < 5.0
+
+
+@pytest.mark.parametrize("q28", [False, True])
+def test_chain_recipes_on_device(oracle, q28):
+    """dsp_recalculate_all_filters() for whole instances: recipes [n][roles][12] -> both internal EQ engines."""
+    fs, n = 48000.0, 21
+    roles = L.CHAINQ_EQ_CHANNELS if q28 else L.CHAIN_EQ_CHANNELS
+    rec = _recipes(n * roles, 77 + q28).reshape(n, roles, L.MAX_BANDS)
+    eng = api.ChainEngineQ28(n, max_frames=96) if q28 else api.ChainEngine("f32f", n, max_frames=96)
+    try:
+        clamped = eng.set_eq_params_device(rec, fs)
+        got = eng.download_biquads()
+    finally:
+        eng.close()
+    want_rec = rec.copy().reshape(-1, L.MAX_BANDS)
+    want = np.zeros((n * roles, L.MAX_BANDS), L.BIQUAD_Q28 if q28 else L.BIQUAD_F32)
+    if q28:
+        want["bypass"] = 1                                # the chain starts with every band bypassed
+    oracle.set_libm_f64(1)
+    try:
+        oracle.eq_coeffs(q28, want_rec, want, fs)
+    finally:
+        oracle.set_libm_f64(0)
+    assert same_bits(clamped.reshape(-1, L.MAX_BANDS), want_rec)
+    assert same_bits(got.reshape(-1, L.MAX_BANDS), want)
