@@ -17,6 +17,7 @@ ap.add_argument("--packets", type=int, default=16)
 ap.add_argument("--fpp", type=int, default=96)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--arith", default="f32f")
+ap.add_argument("--no-sub", action="store_true", help="disable the sub output: no modulator work (isolates the other stages)")
 a = ap.parse_args()
 N, F, fs = a.instances, a.packets * a.fpp, 96000.0
 q28 = a.arith == "q28"
@@ -27,6 +28,8 @@ else:
     P, bq = W.chain_config3(N, fs=fs, seed=1)
     eng = api.ChainEngine(a.arith, N, max_frames=F)
 n_out = 5 if q28 else 9
+if a.no_sub:
+    P["matrix"]["outputs"]["enabled"][:, n_out - 1] = 0
 eng.set_params(P)
 eng.upload_biquads(bq)
 pcm = torch.randint(0, 256, (N, F * 6), dtype=torch.uint8, device="cuda")
