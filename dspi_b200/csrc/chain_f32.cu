@@ -569,24 +569,13 @@ chain_ring_kernel(ChainDev d, uint32_t F, uint32_t fpp)
 // ---------------------------------------------------------------------------------------------
 // delta-sigma PDM (chain_pdm.cuh): one instance per lane
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 chain_pdm_kernel(ChainDev d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
-    // lane carries kPdmPerThread instances: tid, tid + T (T = threads of the launch) - neighbouring lanes stay coalesced
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
-    uint32_t inst[kPdmPerThread];
-    bool active[kPdmPerThread];
-    const int32_t *subq[kPdmPerThread];
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < kPdmPerThread; k++) {
-        inst[k] = tid + k * T;
-        active[k] = inst[k] < d.N && (d.flags[inst[k]] & F_SUB_ON);           // usb_audio.c:944
-        subq[k] = d.subq + (size_t)(active[k] ? inst[k] : 0) * d.ldF;
-        any = any || active[k];
-    }
-    if (!any) return;
-    pdm_modulate_frames<kPdmPerThread>(d.pdm, subq, 1, d.N_pad, inst, active, f_begin, f_end, F, pdm_out);
+    const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= d.N) return;
+    if (!(d.flags[inst] & F_SUB_ON)) return;                                 // usb_audio.c:944
+    pdm_modulate_frames(d.pdm, d.subq + (size_t)inst * d.ldF, 1, d.N_pad, inst, f_begin, f_end, F, pdm_out);
 }
 
 // filters[][] of n instances (instance-major AoS) <-> the mirrors of the two EQ engines (channel = role' * N_pad + inst)
@@ -729,7 +718,7 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
         CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
         // ---- modulator
         CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
-        dspi::chain_pdm_kernel<<<(d.N + 32 * dspi::kPdmPerThread - 1) / (32 * dspi::kPdmPerThread), 32, 0, st.s_pdm>>>(d, fb, fe, F, d_pdm);
+        dspi::chain_pdm_kernel<<<(d.N + 127) / 128, 128, 0, st.s_pdm>>>(d, fb, fe, F, d_pdm);
         CU_OK(cudaGetLastError());
         c->launches += 5;
     }

@@ -7,108 +7,72 @@
 
 namespace dspi {
 
-// Instances per thread.  One instance is ONE serial chain (256 dependent decisions per frame): a warp that
-// carries one instance per lane issues an instruction every ~2.2 cycles (ncu: 0.45 IPC, stall reason `wait`).
-// Two independent instances per lane interleave two such chains in the same instruction stream, which fills
-// the idle issue slots: the same warp does twice the work in about the same time.
-constexpr int kPdmPerThread = 2;
-
 // state words (SoA, [9][Np]): err1 err2 x1 x2 y1 y2 err_acc rng fade_in_pos.
-// Modulates frames [f_begin, f_end) of the K instances inst[k] (active[k] false: that slot is idle - nothing of it
-// is read or written): Q28 samples at subq[k][f * frame_stride], 8 words (256 bits, MSB first) per frame to
-// pdm_out[(inst[k] * F + f) * 8 ..].
-template <int K>
-__device__ __forceinline__ void pdm_modulate_frames(int32_t *__restrict__ pdm, const int32_t *const (&subq)[K], size_t frame_stride, uint32_t Np,
-                                                    const uint32_t (&inst)[K], const bool (&active)[K], uint32_t f_begin, uint32_t f_end, uint32_t F,
-                                                    uint32_t *__restrict__ pdm_out)
+// Modulates frames [f_begin, f_end) of instance `inst`: Q28 samples at subq[f * frame_stride] (the
+// caller offsets `subq` to this instance), 8 words (256 bits, MSB first) per frame to
+// pdm_out[(inst * F + f) * 8 ..].
+__device__ __forceinline__ void pdm_modulate_frames(int32_t *__restrict__ pdm, const int32_t *__restrict__ subq, size_t frame_stride, uint32_t Np,
+                                                    uint32_t inst, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
-    int32_t err1[K], err2[K], x1[K], x2[K], y1[K], y2[K], err_acc[K], q_next[K];
-    uint32_t rng[K], fade[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        err1[k] = err2[k] = x1[k] = x2[k] = y1[k] = y2[k] = err_acc[k] = q_next[k] = 0;
-        rng[k] = 1; fade[k] = 1024;
-        if (active[k]) {
-            const uint32_t i = inst[k];
-            err1[k] = pdm[0 * Np + i]; err2[k] = pdm[1 * Np + i];
-            x1[k] = pdm[2 * Np + i]; x2[k] = pdm[3 * Np + i]; y1[k] = pdm[4 * Np + i]; y2[k] = pdm[5 * Np + i];
-            err_acc[k] = pdm[6 * Np + i];
-            rng[k] = (uint32_t)pdm[7 * Np + i]; fade[k] = (uint32_t)pdm[8 * Np + i];
-            if (f_begin < f_end) q_next[k] = subq[k][(size_t)f_begin * frame_stride];
-        }
-    }
+    int32_t err1 = pdm[0 * Np + inst], err2 = pdm[1 * Np + inst];
+    int32_t x1 = pdm[2 * Np + inst], x2 = pdm[3 * Np + inst], y1 = pdm[4 * Np + inst], y2 = pdm[5 * Np + inst];
+    int32_t err_acc = pdm[6 * Np + inst];
+    uint32_t rng = (uint32_t)pdm[7 * Np + inst], fade = (uint32_t)pdm[8 * Np + inst];
+    int32_t q_next = f_begin < f_end ? subq[(size_t)f_begin * frame_stride] : 0;
     for (uint32_t f = f_begin; f < f_end; f++) {
-        int32_t target[K];
+        int32_t pcm = q_next >> 14;                                          // :352
+        if (f + 1 < f_end) q_next = subq[(size_t)(f + 1) * frame_stride];       // next frame's load overlaps this frame's 256 decisions
+        pcm = max(-29500, min(29500, pcm));                                  // :353-354
+        if (fade < 1024u) { pcm = (pcm * (int32_t)fade) >> 10; fade++; }     // :357-360
+        const int32_t target = pcm + 32768;
+        uint32_t words[8];
 #pragma unroll
-        for (int k = 0; k < K; k++) {
-            int32_t pcm = q_next[k] >> 14;                                   // :352
-            if (active[k] && f + 1 < f_end) q_next[k] = subq[k][(size_t)(f + 1) * frame_stride];   // next frame's load overlaps this frame's 256 decisions
-            pcm = max(-29500, min(29500, pcm));                              // :353-354
-            if (fade[k] < 1024u) { pcm = (pcm * (int32_t)fade[k]) >> 10; fade[k]++; }   // :357-360
-            target[k] = pcm + 32768;
-        }
-        // one 32-decision chunk per iteration, NOT unrolled: 2 x 32 x 6 instructions of straight-line code stay inside
-        // the instruction cache (scripts/pdm_ubench.cu: beyond ~32 KB of loop body the fetch rate collapses)
-#pragma unroll 1
         for (int chunk = 0; chunk < 8; chunk++) {
-            int32_t dither[K], s[K], g[K], tg[K];
-            uint32_t inv[K];                                                 // complement of the output word
+            rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;             // :63-68
+            const int32_t raw = (int32_t)(rng & 0x1FFu) - 255;               // :368
+            err_acc = ((err_acc * 248) >> 8) + ((err2 >> 8) >> 6);           // :92
+            const int32_t in = raw - err_acc;
+            const int32_t dither = (15778 * in - 31556 * x1 + 15778 * x2 + 31531 * y1 - 15580 * y2) >> 14;   // :98-99
+            x2 = x1; x1 = in; y2 = y1; y1 = dither;
+            // :372-378 restated on two running sums so that only TWO dependent integer ops separate
+            // consecutive decisions (the loop is one serial chain per instance, so its depth is the cost):
+            //   s = err2 + dither   (the comparator input)       g = err1 + target
+            //   bit = s >= 0;  s' = s + g - 2*fb;  g' = g + target - fb        (fb = bit ? 65535 : 0)
+            // which is err1 += target - fb; err2 += err1 - fb with the substitutions above (all int32,
+            // wrapping like the reference).  With m = s >> 31 (0 when the bit is 1, -1 when it is 0) the
+            // corrections become m * -K + (sum - K): one shift on the ALU pipe feeding one IMAD on the
+            // FMA pipe per decision.  Measured on B200 with one warp per SM sub-partition
+            // (scripts/pdm_ubench.cu): 13.5 cycles per decision against 18.0 for the mask form,
+            // 20.4 with predicated corrections, 23.4 for the reference's own statement order.
+            uint32_t inv = 0;                                                // complement of the output word
+            int32_t s = err2 + dither;
+            int32_t g = err1 + target;
+            const int32_t tg = target - 65535;
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                rng[k] ^= rng[k] << 13; rng[k] ^= rng[k] >> 17; rng[k] ^= rng[k] << 5;          // :63-68
-                const int32_t raw = (int32_t)(rng[k] & 0x1FFu) - 255;        // :368
-                err_acc[k] = ((err_acc[k] * 248) >> 8) + ((err2[k] >> 8) >> 6);                 // :92
-                const int32_t in = raw - err_acc[k];
-                dither[k] = (15778 * in - 31556 * x1[k] + 15778 * x2[k] + 31531 * y1[k] - 15580 * y2[k]) >> 14;   // :98-99
-                x2[k] = x1[k]; x1[k] = in; y2[k] = y1[k]; y1[k] = dither[k];
-                // :372-378 restated on two running sums so that only TWO dependent integer ops separate
-                // consecutive decisions:
-                //   s = err2 + dither   (the comparator input)       g = err1 + target
-                //   bit = s >= 0;  s' = s + g - 2*fb;  g' = g + target - fb        (fb = bit ? 65535 : 0)
-                // which is err1 += target - fb; err2 += err1 - fb with the substitutions above (all int32,
-                // wrapping like the reference).  With m = s >> 31 (0 when the bit is 1, -1 when it is 0) the
-                // corrections become m * -K + (sum - K): one shift on the ALU pipe feeding one IMAD on the
-                // FMA pipe per decision (scripts/pdm_ubench.cu: 13.5 cycles per decision for one chain per
-                // warp against 18.0 for the mask form, 20.4 with predicated corrections, 23.4 for the
-                // reference's own statement order).
-                inv[k] = 0;
-                s[k] = err2[k] + dither[k];
-                g[k] = err1[k] + target[k];
-                tg[k] = target[k] - 65535;
+            for (int k = 0; k < 32; k++) {
+                const int32_t m = s >> 31;
+                const int32_t t2 = s + g - 2 * 65535;
+                const int32_t g2 = g + tg;
+                inv = __funnelshift_l((uint32_t)s, inv, 1);                  // shift the sign in, MSB first (:375)
+                s = m * (-2 * 65535) + t2;
+                g = m * -65535 + g2;
             }
-#pragma unroll
-            for (int b = 0; b < 32; b++) {
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    const int32_t m = s[k] >> 31;
-                    const int32_t t2 = s[k] + g[k] - 2 * 65535;
-                    const int32_t g2 = g[k] + tg[k];
-                    inv[k] = __funnelshift_l((uint32_t)s[k], inv[k], 1);     // shift the sign in, MSB first (:375)
-                    s[k] = m * (-2 * 65535) + t2;
-                    g[k] = m * -65535 + g2;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                err2[k] = s[k] - dither[k];
-                err1[k] = g[k] - target[k];
-                if (pdm_out && active[k]) pdm_out[((size_t)inst[k] * F + f) * 8 + chunk] = ~inv[k];   // :380
-            }
+            const uint32_t word = ~inv;
+            err2 = s - dither;
+            err1 = g - target;
+            words[chunk] = word;
         }
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            err1[k] -= err1[k] >> 16;                                        // :396-397
-            err2[k] -= err2[k] >> 16;
+        err1 -= err1 >> 16;                                                  // :396-397
+        err2 -= err2 >> 16;
+        if (pdm_out) {
+            uint4 *dst = reinterpret_cast<uint4 *>(pdm_out + ((size_t)inst * F + f) * 8);
+            dst[0] = make_uint4(words[0], words[1], words[2], words[3]);
+            dst[1] = make_uint4(words[4], words[5], words[6], words[7]);
         }
     }
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        if (!active[k]) continue;
-        const uint32_t i = inst[k];
-        pdm[0 * Np + i] = err1[k]; pdm[1 * Np + i] = err2[k];
-        pdm[2 * Np + i] = x1[k]; pdm[3 * Np + i] = x2[k]; pdm[4 * Np + i] = y1[k]; pdm[5 * Np + i] = y2[k];
-        pdm[6 * Np + i] = err_acc[k]; pdm[7 * Np + i] = (int32_t)rng[k]; pdm[8 * Np + i] = (int32_t)fade[k];
-    }
+    pdm[0 * Np + inst] = err1; pdm[1 * Np + inst] = err2;
+    pdm[2 * Np + inst] = x1; pdm[3 * Np + inst] = x2; pdm[4 * Np + inst] = y1; pdm[5 * Np + inst] = y2;
+    pdm[6 * Np + inst] = err_acc; pdm[7 * Np + inst] = (int32_t)rng; pdm[8 * Np + inst] = (int32_t)fade;
 }
 
 }  // namespace dspi

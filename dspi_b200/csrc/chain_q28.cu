@@ -515,23 +515,13 @@ chainq_ring_kernel(ChainQ d, uint32_t F)
     }
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 chainq_pdm_kernel(ChainQ d, uint32_t f_begin, uint32_t f_end, uint32_t F, uint32_t *__restrict__ pdm_out)
 {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
-    uint32_t inst[kPdmPerThread];
-    bool active[kPdmPerThread];
-    const int32_t *subq[kPdmPerThread];
-    bool any = false;
-#pragma unroll
-    for (int k = 0; k < kPdmPerThread; k++) {
-        inst[k] = tid + k * T;
-        active[k] = inst[k] < d.N && (d.flags[inst[k]] & F_SUB_ON);           // usb_audio.c:1261
-        subq[k] = d.subq + (size_t)(active[k] ? inst[k] : 0) * d.ldF;
-        any = any || active[k];
-    }
-    if (!any) return;
-    pdm_modulate_frames<kPdmPerThread>(d.pdm, subq, 1, d.N_pad, inst, active, f_begin, f_end, F, pdm_out);
+    const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= d.N) return;
+    if (!(d.flags[inst] & F_SUB_ON)) return;                                                              // usb_audio.c:1261
+    pdm_modulate_frames(d.pdm, d.subq + (size_t)inst * d.ldF, 1, d.N_pad, inst, f_begin, f_end, F, pdm_out);
 }
 
 // filters[][] of n instances (instance-major AoS, 32-byte records) <-> the mirrors of the two EQ engines
@@ -956,7 +946,7 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
         CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
-        dspi::chainq_pdm_kernel<<<(d.N + 32 * dspi::kPdmPerThread - 1) / (32 * dspi::kPdmPerThread), 32, 0, st.s_pdm>>>(d, fb, fe, F, d_pdm);
+        dspi::chainq_pdm_kernel<<<(d.N + 127) / 128, 128, 0, st.s_pdm>>>(d, fb, fe, F, d_pdm);
         CU_OK(cudaGetLastError());
         c->launches += 5;
     }
