@@ -22,6 +22,7 @@ SYMBOLS = [
     "dspi_eq_create", "dspi_eq_destroy", "dspi_eq_upload_biquads", "dspi_eq_download_biquads", "dspi_eq_set_param",
     "dspi_eq_process_device", "dspi_eq_process_host", "dspi_eq_sync", "dspi_eq_stream", "dspi_eq_launch_count",
     "dspi_eq_kernel_info", "dspi_eq_set_params_device", "dspi_chain_set_eq_params_device", "dspi_chainq_set_eq_params_device",
+    "dspi_chain_state_size", "dspi_chain_state_export", "dspi_chain_state_import", "dspi_chainq_state_size", "dspi_chainq_state_export", "dspi_chainq_state_import",
     "dspi_host_alloc", "dspi_host_free",
     "dspi_chain_create", "dspi_chain_destroy", "dspi_chain_set_params", "dspi_chain_upload_biquads", "dspi_chain_download_biquads",
     "dspi_chain_reset_state", "dspi_chain_process_host", "dspi_chain_process_device", "dspi_chain_sync", "dspi_chain_stream",
@@ -279,6 +280,19 @@ class ChainEngine:
         _check(lib().dspi_chain_download_biquads(self._h, inst0, n, out.ctypes.data))
         return out
 
+    def state_export(self):
+        """Checkpoint: filter / leveller / delay / modulator state (and coefficients) as one bytes-like blob."""
+        fn = getattr(lib(), "dspi_chain_state_size")
+        fn.restype = C.c_size_t
+        n = int(fn(self._h))
+        blob = np.zeros(n, np.uint8)
+        _check(getattr(lib(), "dspi_chain_state_export")(self._h, blob.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+        return blob
+
+    def state_import(self, blob):
+        b = np.ascontiguousarray(blob, np.uint8)
+        _check(getattr(lib(), "dspi_chain_state_import")(self._h, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size)))
+
     def reset_state(self):
         _check(lib().dspi_chain_reset_state(self._h))
 
@@ -482,6 +496,19 @@ class ChainEngineQ28:
         out = np.zeros((n, L.CHAINQ_EQ_CHANNELS, L.MAX_BANDS), L.BIQUAD_Q28)
         _check(lib().dspi_chainq_download_biquads(self._h, inst0, n, out.ctypes.data))
         return out
+
+    def state_export(self):
+        """Checkpoint: filter / leveller / delay / modulator state (and coefficients) as one bytes-like blob."""
+        fn = getattr(lib(), "dspi_chainq_state_size")
+        fn.restype = C.c_size_t
+        n = int(fn(self._h))
+        blob = np.zeros(n, np.uint8)
+        _check(getattr(lib(), "dspi_chainq_state_export")(self._h, blob.ctypes.data_as(C.c_void_p), C.c_size_t(n)))
+        return blob
+
+    def state_import(self, blob):
+        b = np.ascontiguousarray(blob, np.uint8)
+        _check(getattr(lib(), "dspi_chainq_state_import")(self._h, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size)))
 
     def reset_state(self):
         _check(lib().dspi_chainq_reset_state(self._h))

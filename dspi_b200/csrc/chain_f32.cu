@@ -1047,6 +1047,84 @@ int dspi_chain_process_host(dspi_chain *c, const void *pcm, uint32_t bit_depth, 
     return DSPI_OK;
 }
 
+
+// ---- checkpoint / resume: everything a later process call depends on besides the parameters ----------------
+static void state_sections(dspi_chain *c, std::vector<std::pair<void *, size_t>> &v)
+{
+    const size_t Np = c->d.N_pad;
+    v.push_back({ c->d.loud_st, 8 * Np * 4 });
+    v.push_back({ c->d.xf, 7 * Np * 4 });                                  // crossfeed coefficients and state (CrossfeedState)
+    v.push_back({ c->d.lev_s, 5 * Np * 4 });
+    v.push_back({ c->d.lev_idx, Np * 4 });
+    v.push_back({ c->d.lev_la, (size_t)2 * dspi::kLa * Np * 4 });
+    v.push_back({ c->d.dline, (size_t)dspi::kOuts * dspi::kMaxDelay * Np * 4 });
+    v.push_back({ c->d.widx_in, Np * 4 });
+    v.push_back({ c->d.pdm, 9 * Np * 4 });
+    v.push_back({ c->d.peaks, (size_t)dspi::kRoles * Np * 2 });
+    v.push_back({ c->d.clip, Np * 2 });
+    dspi::eq_state_sections(c->eq_m, v);
+    dspi::eq_state_sections(c->eq_o, v);
+}
+
+struct StateHeader { uint32_t magic, version, arith, n_instances, n_bands, n_sections; uint64_t bytes; };
+static const uint32_t kStateMagic = 0x53505344u;          // "DSPS"
+
+size_t dspi_chain_state_size(dspi_chain *c)
+{
+    if (!c) return 0;
+    std::vector<std::pair<void *, size_t>> v;
+    state_sections(c, v);
+    size_t n = sizeof(StateHeader);
+    for (auto &s : v) n += s.second;
+    return n;
+}
+
+int dspi_chain_state_export(dspi_chain *c, void *blob, size_t cap)
+{
+    if (!c || !blob) return fail(DSPI_EINVAL, "null argument");
+    const size_t need = dspi_chain_state_size(c);
+    if (cap < need) return fail(DSPI_ERANGE, "state blob needs %zu bytes, %zu given", need, cap);
+    CU_OK(cudaSetDevice(c->desc.device));
+    std::vector<std::pair<void *, size_t>> v;
+    state_sections(c, v);
+    StateHeader h = { kStateMagic, 1u, c->desc.arith, c->desc.n_instances, c->desc.n_bands, (uint32_t)v.size(), (uint64_t)need };
+    memcpy(blob, &h, sizeof(h));
+    char *p = (char *)blob + sizeof(h);
+    for (auto &s : v) {
+        CU_OK(cudaMemcpyAsync(p, s.first, s.second, cudaMemcpyDeviceToHost, c->stream));
+        p += s.second;
+    }
+    CU_OK(cudaStreamSynchronize(c->stream));
+    return DSPI_OK;
+}
+
+int dspi_chain_state_import(dspi_chain *c, const void *blob, size_t len)
+{
+    if (!c || !blob) return fail(DSPI_EINVAL, "null argument");
+    std::vector<std::pair<void *, size_t>> v;
+    state_sections(c, v);
+    StateHeader h;
+    if (len < sizeof(h)) return fail(DSPI_EINVAL, "state blob too short");
+    memcpy(&h, blob, sizeof(h));
+    if (h.magic != kStateMagic || h.version != 1u) return fail(DSPI_EINVAL, "not a dspi_b200 state blob (magic %08x version %u)", h.magic, h.version);
+    if (h.arith != c->desc.arith || h.n_instances != c->desc.n_instances || h.n_bands != c->desc.n_bands || h.n_sections != v.size() ||
+        h.bytes != dspi_chain_state_size(c) || len < h.bytes)
+        return fail(DSPI_EINVAL, "state blob belongs to a different engine shape (%u instances, arith %u, %llu bytes)", h.n_instances, h.arith,
+                    (unsigned long long)h.bytes);
+    CU_OK(cudaSetDevice(c->desc.device));
+    const char *p = (const char *)blob + sizeof(h);
+    for (auto &s : v) {
+        CU_OK(cudaMemcpyAsync(s.first, p, s.second, cudaMemcpyHostToDevice, c->stream));
+        p += s.second;
+    }
+    CU_OK(cudaStreamSynchronize(c->stream));
+    int rc = dspi::eq_state_imported(c->eq_m, c->stream);
+    if (rc == DSPI_OK) rc = dspi::eq_state_imported(c->eq_o, c->stream);
+    if (rc) return rc;
+    CU_OK(cudaStreamSynchronize(c->stream));
+    return DSPI_OK;
+}
+
 int dspi_chain_sync(dspi_chain *c)
 {
     if (!c) return fail(DSPI_EINVAL, "null argument");

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <algorithm>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "eq_kernels.cuh"
@@ -456,6 +457,22 @@ int eq_set_skip(dspi_eq *e, const uint8_t *d_skip, cudaStream_t s)
     if (rc) return rc;
     CU_OK(cudaStreamSynchronize(s));
     return DSPI_OK;
+}
+
+// the device arrays that make up an engine's coefficient + filter state (checkpointing by the chain engines)
+void eq_state_sections(dspi_eq *e, std::vector<std::pair<void *, size_t>> &out)
+{
+    const bool q28 = e->desc.arith == DSPI_ARITH_Q28;
+    const size_t coef_bytes = q28 ? (size_t)e->n_groups * DSPI_MAX_BANDS * 20 * 32 * 4 : (size_t)e->c_pad * DSPI_MAX_BANDS * 8 * 4;
+    out.push_back({ e->d_coef, coef_bytes });
+    if (e->d_modes) out.push_back({ e->d_modes, (size_t)e->c_pad * 8 });
+}
+
+// after the sections were overwritten: effective topology words and the kernel choice must be re-derived
+int eq_state_imported(dspi_eq *e, cudaStream_t s)
+{
+    e->sig_dirty = true;
+    return remask(e, s);
 }
 
 int eq_process_on(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStream_t s)

@@ -1,5 +1,8 @@
 // eq_kernels.cuh — declarations shared by the EQ kernels and the engine (C-ABI) code.
 #pragma once
+#include <utility>
+#include <vector>
+
 #include "eq_modes.cuh"
 #include "dspi_b200.h"
 
@@ -50,6 +53,8 @@ int eq_unpack_range(dspi_eq *e, uint32_t ch0, uint32_t n, cudaStream_t s); // pa
 // device memory owned by the caller; call again after changing it.
 int eq_set_skip(dspi_eq *e, const uint8_t *d_skip, cudaStream_t s);
 int eq_process_on(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStream_t s);
+void eq_state_sections(dspi_eq *e, std::vector<std::pair<void *, size_t>> &out);   // coefficient + state store (and topology words)
+int eq_state_imported(dspi_eq *e, cudaStream_t s);
 // coeff.cu: dsp_compute_coefficients() for channels [ch0, ch0 + n) of a mirror, recipes [n][12] on the device (clamped in place)
 cudaError_t launch_coeffs(bool q28, dspi_eq_param *d_recipes, void *d_aos, uint32_t ch0, uint32_t n, float fs, cudaStream_t stream);
 cudaError_t launch_skip_q28(int32_t *coef, const uint8_t *skip, uint32_t n, cudaStream_t stream);

@@ -251,6 +251,13 @@ int dspi_chain_set_eq_params_device(dspi_chain *c, uint32_t inst0, uint32_t n, d
 /* pipeline reset: clears leveller, loudness, delay-line and PDM state (leveller_reset_state(),
  * pdm_processing_loop() restart path); filter state is part of the biquads */
 int dspi_chain_reset_state(dspi_chain *c);
+/* Checkpoint / resume (the dspi_state_export/import of SURVEY 8 b): everything a later process call depends on besides
+ * dspi_chain_set_params' records - filter coefficients and state, loudness / crossfeed / leveller state, look-ahead and
+ * delay rings, write index, modulator state, meters.  The blob is private to this library (header + raw arrays) and only
+ * loads into an engine of the same shape. */
+size_t dspi_chain_state_size(dspi_chain *c);
+int dspi_chain_state_export(dspi_chain *c, void *blob, size_t cap);
+int dspi_chain_state_import(dspi_chain *c, const void *blob, size_t len);
 /* n_packets USB packets of frames_per_packet (<= 192) frames for every instance.
  *   pcm:       [n_instances][n_packets * frames_per_packet] interleaved L,R little-endian frames,
  *              bit_depth 16 (4 bytes / frame) or 24 (packed, 6 bytes / frame)      (HOST memory)
@@ -319,6 +326,9 @@ int dspi_chainq_upload_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, const
 int dspi_chainq_download_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_biquad_q28 *biquads);
 int dspi_chainq_set_eq_params_device(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_eq_param *recipes, float sample_rate);   /* recipes[n][7][12] */
 int dspi_chainq_reset_state(dspi_chainq *c);
+size_t dspi_chainq_state_size(dspi_chainq *c);
+int dspi_chainq_state_export(dspi_chainq *c, void *blob, size_t cap);
+int dspi_chainq_state_import(dspi_chainq *c, const void *blob, size_t len);
 /* pcm as for dspi_chain_process_host; spdif_out [n_instances][2][n_frames][2]; pdm_out [n_instances][n_frames][8] */
 int dspi_chainq_process_host(dspi_chainq *c, const void *pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t frames_per_packet,
                              int32_t *spdif_out, uint32_t *pdm_out, dspi_status_q28 *status);
