@@ -684,10 +684,11 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
     const uint32_t F = n_packets * fpp;
     auto post = dspi::chain_post_kernel<FUSED>;
     const size_t post_smem = (size_t)4 * 2 * fpp * dspi::kXs * 4;           // 4 warps x (packet + look-ahead columns)
-    static size_t post_smem_set = 0;
-    if (post_smem > post_smem_set) {
+    static dspi::PerDeviceOnce once;                                // per instantiation (flavour)
+    int dev = 0;
+    if (once.needs(&dev)) {
         CU_OK(cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * 2 * dspi::kPkt * dspi::kXs * 4)));
-        post_smem_set = (size_t)4 * 2 * dspi::kPkt * dspi::kXs * 4;
+        once.mark(dev);
     }
     // Stage pipeline over packet slices on three streams (chain_streams.cuh): front stages of slice
     // i+1 overlap the output stages of slice i and the modulator of slice i-1.

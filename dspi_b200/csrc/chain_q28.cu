@@ -916,10 +916,11 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
     CU_OK(cudaSetDevice(c->desc.device));
     const uint32_t F = n_packets * fpp;
     const size_t post_smem = (size_t)4 * 2 * fpp * dspi::kXs * 4;           // 4 warps x (packet + look-ahead columns)
-    static bool configured = false;
-    if (!configured) {
+    static dspi::PerDeviceOnce once;
+    int dev = 0;
+    if (once.needs(&dev)) {
         CU_OK(cudaFuncSetAttribute(dspi::chainq_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * 2 * dspi::kPkt * dspi::kXs * 4)));
-        configured = true;
+        once.mark(dev);
     }
     // Stage pipeline over packet slices on three streams (chain_streams.cuh), stages as in chain_f32.cu.
     dspi::ChainStreams &st = c->st;

@@ -49,12 +49,13 @@ cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
     constexpr size_t smem = (size_t)kWarps * kStages * (32 * CPL) * kTileT * 4;
     auto kern = eq_f32_kernel<V, FUSED, NB, false>;
     auto kern_dyn = eq_f32_kernel<V, FUSED, NB, true>;
-    static bool configured = false;                             // per instantiation
-    if (!configured) {
+    static PerDeviceOnce once;                                  // per instantiation
+    int dev = 0;
+    if (once.needs(&dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern_dyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        once.mark(dev);
     }
     const uint32_t n_groups = a.n_groups;
     uint32_t grid = (n_groups + kWarps - 1) / kWarps;

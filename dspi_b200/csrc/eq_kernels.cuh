@@ -26,6 +26,19 @@ struct EqLaunch {
     int n_sms;             // SM count of the device
 };
 
+// cudaFuncSetAttribute is per device: remembers, per kernel (one flag word per call site), which devices are done
+struct PerDeviceOnce {
+    unsigned long long done = 0;
+    bool needs(int *device_out)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        *device_out = dev;
+        return dev < 0 || dev >= 64 || !((done >> dev) & 1ull);
+    }
+    void mark(int dev) { if (dev >= 0 && dev < 64) done |= 1ull << dev; }
+};
+
 // per-thread message buffer behind dspi_last_error() (engine.cu)
 char *error_buffer(size_t *cap);
 

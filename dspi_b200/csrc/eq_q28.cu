@@ -222,11 +222,12 @@ cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
 {
     constexpr size_t smem = (size_t)kWarps * kStages * kStageBytes;
     auto kern = eq_q28_kernel<NB>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    int dev = 0;
+    if (once.needs(&dev)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        once.mark(dev);
     }
     const uint32_t grid = (a.n_groups + kWarps - 1) / kWarps;
     kern<<<grid, kWarps * 32, smem, stream>>>(a.tmap, (int32_t *)a.samples, a.ld, (int32_t *)a.coef, a.n_groups, a.n_rows, a.T, a.n_bands, a.use_tma);
