@@ -34,6 +34,7 @@ SYMBOLS = [
     "dspi_spdif_lookup_table", "dspi_spdif_encode_device", "dspi_spdif_encode_host",
     "dspi_bulk_state_defaults", "dspi_bulk_params_apply", "dspi_bulk_params_collect", "dspi_bulk_state_to_chain_f32", "dspi_bulk_state_to_chain_q28",
     "dspi_preset_slot_size", "dspi_crc32", "dspi_preset_slot_apply", "dspi_preset_slot_collect",
+    "dspi_preamp", "dspi_master_volume", "dspi_preset_mute_arm", "dspi_preset_mute_step",
 ]
 
 
@@ -113,6 +114,11 @@ def lib():
         h.dspi_loudness_compute_table_f32.argtypes = [vp, C.c_float, C.c_float, C.c_float]
         h.dspi_host_volume.argtypes = [C.c_int16, vp]
         h.dspi_host_volume.restype = C.c_int16
+        h.dspi_preamp.argtypes = [C.c_float, vp, vp]
+        h.dspi_master_volume.argtypes = [C.c_float, vp, vp]
+        h.dspi_preset_mute_arm.argtypes = [vp, u32]
+        h.dspi_preset_mute_step.argtypes = [vp, u32, u32]
+        h.dspi_preset_mute_step.restype = C.c_float
         h.dspi_host_alloc.argtypes = [C.c_size_t]
         h.dspi_host_alloc.restype = vp
         h.dspi_host_free.argtypes = [vp]
@@ -453,6 +459,22 @@ def host_volume(volume_8_8):
     idx = C.c_uint8()
     v = lib().dspi_host_volume(int(volume_8_8), C.byref(idx))
     return int(v), int(idx.value)
+
+
+def preamp(db):
+    """``update_preamp``: (linear float, Q28 int)."""
+    lin, q = C.c_float(), C.c_int32()
+    if lib().dspi_preamp(float(db), C.byref(lin), C.byref(q)) != 0:
+        raise DspiError("preamp: NaN / Inf rejected")
+    return lin.value, q.value
+
+
+def master_volume(db):
+    """``update_master_volume``: (linear float, Q15 int)."""
+    lin, q = C.c_float(), C.c_int32()
+    if lib().dspi_master_volume(float(db), C.byref(lin), C.byref(q)) != 0:
+        raise DspiError("master volume: NaN / Inf rejected")
+    return lin.value, q.value
 
 
 class ChainEngineQ28:

@@ -320,6 +320,68 @@ int16_t dspi_host_volume(int16_t volume_8_8, uint8_t *table_index)
     return (int16_t)q15[idx];                                               /* stored in an int16_t: 0 dB -> -32768 */
 }
 
+/* update_preamp(), usb_audio.c:244-250: dB -> the float and the Q28 gain the packet loop reads.  NaN / Inf are
+ * rejected as there (returns -1, outputs untouched).  The Q28 conversion saturates like the Cortex-M VCVT. */
+int dspi_preamp(float db, float *linear_out, int32_t *q28_out)
+{
+    if (!isfinite(db)) return -1;
+    const float linear = powf(10.0f, db / 20.0f);
+    const float scaled = linear * (float)(1 << 28);
+    if (linear_out) *linear_out = linear;
+    if (q28_out) *q28_out = scaled >= 2147483648.0f ? INT32_MAX : (int32_t)scaled;
+    return 0;
+}
+
+/* update_master_volume(), usb_audio.c:255-269: clamp to [-128, 0] dB, -128 is the mute sentinel */
+int dspi_master_volume(float db, float *linear_out, int32_t *q15_out)
+{
+    if (!isfinite(db)) return -1;
+    if (db < -128.0f) db = -128.0f;
+    if (db > 0.0f) db = 0.0f;
+    float linear = 0.0f;
+    int32_t q15 = 0;
+    if (db > -128.0f) {
+        linear = powf(10.0f, db / 20.0f);
+        q15 = (int32_t)(linear * 32768.0f);
+    }
+    if (linear_out) *linear_out = linear;
+    if (q15_out) *q15_out = q15;
+    return 0;
+}
+
+/* update_preset_mute_envelope(), usb_audio.c:456-498, for one packet of `sample_count` frames: the state is
+ * {preset_loading, preset_mute_counter (flash_storage.c:255-256), preset_mute_smooth_gain}; returns the gain
+ * process_audio_packet() multiplies into the host volume.  dspi_preset_mute_arm() is what every flash-backed
+ * operation does first (flash_storage.c:272-276, 347-348, 775-776): hold for max(512, 10 ms) samples. */
+void dspi_preset_mute_arm(dspi_preset_mute *m, uint32_t sample_rate_hz)
+{
+    uint64_t samples = ((uint64_t)sample_rate_hz * 10u + 999u) / 1000u;
+    if (samples < 512u) samples = 512u;
+    m->counter = (uint32_t)samples;
+    m->loading = 1;
+}
+
+float dspi_preset_mute_step(dspi_preset_mute *m, uint32_t sample_count, uint32_t sample_rate_hz)
+{
+    const int active = m->loading != 0;                                     /* :469 latched for this packet */
+    if (active) {
+        if (m->counter > sample_count) m->counter -= sample_count;
+        else { m->counter = 0; m->loading = 0; }
+    }
+    const float target = active ? 0.0f : 1.0f;
+    if (sample_count == 0) { m->smooth_gain = target; return target; }
+    uint64_t ts = ((uint64_t)sample_rate_hz * 8u + 999u) / 1000u;           /* PRESET_MUTE_TRANSITION_MS 8 */
+    if (ts < 1u) ts = 1u;
+    if (ts > UINT32_MAX) ts = UINT32_MAX;
+    float step = (float)sample_count / (float)(uint32_t)ts;
+    if (step > 1.0f) step = 1.0f;
+    float g = m->smooth_gain;
+    if (g < target)      { g += step; if (g > target) g = target; }
+    else if (g > target) { g -= step; if (g < target) g = target; }
+    m->smooth_gain = g;
+    return g;
+}
+
 /* ---- Q28 stores (RP2040 build of the same parameter functions) -------------------------------- */
 
 void dspi_crossfeed_compute_coefficients_q28(dspi_crossfeed_state_q28 *st, const dspi_crossfeed_config *cfg, float fs)

@@ -227,6 +227,20 @@ void dspi_crossfeed_compute_coefficients_f32(dspi_crossfeed_state_f32 *st, const
 void dspi_leveller_compute_coefficients(dspi_leveller_coeffs *out, const dspi_leveller_config *cfg, float sample_rate);
 void dspi_loudness_compute_table_f32(dspi_loudness_coeffs_f32 table[61][2], float ref_spl, float intensity_pct, float sample_rate);
 int16_t dspi_host_volume(int16_t volume_8_8, uint8_t *table_index);
+/* update_preamp() usb_audio.c:244-250 and update_master_volume() :255-269: dB -> the gains the packet loop reads
+ * (float for the RP2350 shape, Q28 / Q15 for the RP2040 shape).  Return -1 for NaN / Inf like the firmware's guard. */
+int dspi_preamp(float db, float *linear_out, int32_t *q28_out);
+int dspi_master_volume(float db, float *linear_out, int32_t *q15_out);
+/* The preset-mute envelope, update_preset_mute_envelope() usb_audio.c:456-498: state of one instance and its
+ * per-packet step (host side; dspi_chain(q)_set_preset_mute runs the same recurrence on the device). */
+typedef struct {
+    uint8_t  loading;                /* preset_loading, flash_storage.c:255                          */
+    uint8_t  reserved[3];
+    uint32_t counter;                /* preset_mute_counter, flash_storage.c:256                     */
+    float    smooth_gain;            /* preset_mute_smooth_gain, usb_audio.c:457 (1.0 = full level)  */
+} dspi_preset_mute;
+void  dspi_preset_mute_arm(dspi_preset_mute *m, uint32_t sample_rate_hz);    /* flash_storage.c:272-276, 347-348 */
+float dspi_preset_mute_step(dspi_preset_mute *m, uint32_t sample_count, uint32_t sample_rate_hz);
 
 typedef struct dspi_chain dspi_chain;
 typedef struct {

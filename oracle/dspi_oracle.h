@@ -165,6 +165,13 @@ typedef struct {
     orc_pdm_state pdm;
     uint16_t peaks[ORC_MAX_EQ_CH];
     uint16_t clip_flags;
+    /* preset-mute envelope (usb_audio.c:457-498, flash_storage.c:255-256).  mute_env_on == 0: the packet uses
+     * preset_mute_gain above as given (a caller-computed constant); != 0: the envelope below runs once per
+     * packet exactly as update_preset_mute_envelope() and preset_mute_gain is overwritten with its result. */
+    uint8_t  mute_env_on, preset_loading, pad3[2];
+    uint32_t preset_mute_counter;
+    float    preset_mute_smooth_gain;
+    uint32_t sample_rate_hz;
 } orc_chain_f32;
 
 typedef struct {
@@ -194,6 +201,13 @@ typedef struct {
     orc_pdm_state pdm;
     uint16_t peaks[ORC_MAX_EQ_CH];
     uint16_t clip_flags;
+    /* preset-mute envelope (usb_audio.c:457-498, flash_storage.c:255-256).  mute_env_on == 0: the packet uses
+     * preset_mute_gain above as given (a caller-computed constant); != 0: the envelope below runs once per
+     * packet exactly as update_preset_mute_envelope() and preset_mute_gain is overwritten with its result. */
+    uint8_t  mute_env_on, preset_loading, pad3[2];
+    uint32_t preset_mute_counter;
+    float    preset_mute_smooth_gain;
+    uint32_t sample_rate_hz;
 } orc_chain_q28;
 
 /* ---- control -------------------------------------------------------------- */
@@ -252,6 +266,10 @@ void orc_q28_leveller(orc_lev_state_q28 *st, const orc_lev_coeffs *c, int lookah
 void orc_spdif_lookup_init(uint32_t table[256]);                                                  /* audio_spdif.c:141-153 */
 void orc_spdif_update_subframe(const uint32_t table[256], uint32_t *l, uint32_t *h, int32_t sample);  /* sample_encoding.h:27-50 */
 void orc_spdif_encode(const uint32_t table[256], const int32_t *words, uint32_t frames, uint32_t pos0, const uint8_t cs[5], uint32_t *out);
+
+/* usb_audio.c:459-498 update_preset_mute_envelope(): one packet of `sample_count` frames; returns the gain */
+float orc_mute_envelope(uint8_t *preset_loading, uint32_t *preset_mute_counter, float *smooth_gain,
+                        uint32_t sample_count, uint32_t sample_rate_hz);
 
 void orc_pdm_reset(orc_pdm_state *st);
 void orc_pdm_modulate(orc_pdm_state *st, int32_t sample_q28, uint32_t out[8]);  /* pdm_generator.c:351-397 */

@@ -383,3 +383,26 @@ int16_t orc_host_vol_mul(int16_t volume, uint8_t *vol_index_out)
     if (vol_index_out) *vol_index_out = idx;
     return (int16_t)db_to_vol[idx];
 }
+
+/* usb_audio.c:456-498 — preset-mute envelope, advanced once per packet */
+float orc_mute_envelope(uint8_t *preset_loading, uint32_t *preset_mute_counter, float *smooth_gain,
+                        uint32_t sample_count, uint32_t sample_rate_hz)
+{
+    const int mute_active_for_packet = *preset_loading != 0;                      /* :469 */
+    if (mute_active_for_packet) {
+        if (*preset_mute_counter > sample_count) *preset_mute_counter -= sample_count;   /* :472-473 */
+        else { *preset_mute_counter = 0; *preset_loading = 0; }                   /* :475-476 */
+    }
+    const float target = mute_active_for_packet ? 0.0f : 1.0f;                    /* :480 */
+    if (sample_count == 0) { *smooth_gain = target; return target; }              /* :481-484 */
+    uint64_t ts = ((uint64_t)sample_rate_hz * 8u + 999u) / 1000u;                 /* :459-464, PRESET_MUTE_TRANSITION_MS = 8 */
+    if (ts < 1u) ts = 1u;
+    if (ts > 0xFFFFFFFFu) ts = 0xFFFFFFFFu;
+    float step = (float)sample_count / (float)(uint32_t)ts;                       /* :486 */
+    if (step > 1.0f) step = 1.0f;
+    float g = *smooth_gain;
+    if (g < target)      { g += step; if (g > target) g = target; }               /* :489-491 */
+    else if (g > target) { g -= step; if (g < target) g = target; }               /* :492-494 */
+    *smooth_gain = g;
+    return g;
+}

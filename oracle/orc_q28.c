@@ -300,6 +300,9 @@ uint32_t orc_q28_chain_packet(orc_chain_q28 *in, const uint8_t *data, uint32_t d
     const uint32_t O = in->n_out;
     const uint32_t mask = in->max_delay - 1;
 
+    if (in->mute_env_on)                                                 /* :532 */
+        in->preset_mute_gain = orc_mute_envelope(&in->preset_loading, &in->preset_mute_counter, &in->preset_mute_smooth_gain,
+                                                 data_len / ((bit_depth == 24) ? 6u : 4u), in->sample_rate_hz);
     int32_t vol_mul = in->host_mute ? 0 : (int32_t)in->host_vol_mul;                    /* :975 */
     int32_t pmg = (int32_t)(in->preset_mute_gain * 32768.0f + 0.5f);                    /* :976 */
     if (pmg < 0) pmg = 0;

@@ -1,0 +1,3 @@
+/* stand-in, see fw_stub.h (test infrastructure) */
+#pragma once
+#include "fw_stub.h"

@@ -134,3 +134,111 @@ def chain_params_q28(oracle, N, fs, seed, leveller=True):
         if i % 7 == 3:
             bq[i, 4]["bypass"] = 1
     return P, bq
+
+
+def pcm_bytes_full_scale(F, bit_depth, seed):
+    """One instance, every code of the format reachable (incl. the most negative one)."""
+    rng = np.random.default_rng(seed)
+    if bit_depth == 16:
+        s = rng.integers(-32768, 32768, (F, 2)).astype("<i2")
+        s[::17, 0] = -32768
+        s[5::19, 1] = 32767
+        return s.view(np.uint8).reshape(F * 4)
+    s = rng.integers(-(1 << 23), 1 << 23, (F, 2)).astype(np.int32)
+    s[::17, 0] = -(1 << 23)
+    s[5::19, 1] = (1 << 23) - 1
+    b = np.zeros((F, 2, 3), np.uint8)
+    b[..., 0] = s & 0xFF
+    b[..., 1] = (s >> 8) & 0xFF
+    b[..., 2] = (s >> 16) & 0xFF
+    return b.reshape(F * 6)
+
+
+QUIRK_CASES = ["full_volume_polarity", "delay_equals_max", "delay_max_minus_one", "clipping_hot_input", "pdm_saturation",
+               "host_muted", "everything_off", "sub_only"]
+
+
+def quirk_cases(oracle, flavour, case, fs, F):
+    """(params record, biquads, pcm bytes, bit depth) of one instance that exercises one documented quirk
+    (SURVEY §8 'quirks', VERDICT r1 'quirks not exercised')."""
+    q = flavour == "q28"
+    if q:
+        P, bq = chain_params_q28(oracle, 1, fs, 31)
+        n_out, max_delay = 5, 2048
+    else:
+        P, bq = chain_params(oracle, 1, fs, 32, uniform=True)
+        n_out, max_delay = 9, 4096
+    p = P[0]
+    m = p["matrix"]
+    p["host_mute"] = 0
+    p["preset_mute_gain"] = 1.0
+    for o in range(n_out):
+        m["outputs"][o]["enabled"] = 1
+        m["outputs"][o]["mute"] = 0
+    bit_depth = 24
+    pcm = pcm_bytes(1, F, bit_depth, 9)[0]
+
+    def set_master(db):
+        lin, q15 = api.master_volume(db)
+        if q:
+            p["master_volume_q15"] = q15
+        else:
+            p["master_volume_linear"] = lin
+
+    def set_preamp(db):
+        lin, q28 = api.preamp(db)
+        if q:
+            p["preamp_q28"] = [q28, q28]
+        else:
+            p["preamp_linear"] = [lin, lin]
+
+    if case == "full_volume_polarity":
+        # quirk 1: 0 dB host volume -> vol_mul = (int16)0x8000 = -32768 -> gain -1.0 / Q15 -32768
+        vm, row = api.host_volume(0)
+        assert vm == -32768
+        p["host_vol_mul"] = vm
+        tab = api.loudness_table_q28(fs, 83.0, 100.0) if q else api.loudness_table(fs, 83.0, 100.0)
+        p["loudness"] = tab[row]
+        set_master(0.0)
+    elif case in ("delay_equals_max", "delay_max_minus_one"):
+        # dly == MAX_DELAY_SAMPLES aliases to zero delay through the ring mask (dsp_pipeline.c:232-236 clamps to MAX)
+        d = max_delay if case == "delay_equals_max" else max_delay - 1
+        for o in range(n_out):
+            m["outputs"][o]["delay_samples"] = d if o % 2 == 0 else (d - 1 if o % 3 else 0)
+    elif case == "clipping_hot_input":
+        pcm = pcm_bytes_full_scale(F, 16, 13)
+        bit_depth = 16
+        set_preamp(6.0)
+        set_master(0.0)
+        p["host_vol_mul"] = api.host_volume(-256)[0]      # -1 dB: 0x7215
+        p["leveller_enabled"] = 0
+        for o in range(n_out):
+            m["outputs"][o]["gain_db"] = np.float32(3.0)
+            m["outputs"][o]["gain_linear"] = np.float32(10.0 ** (3.0 / 20.0))
+    elif case == "pdm_saturation":
+        # quirk 7: (int32)(x * 2^28) for |x| >= 8 (float path) / wrapping Q15 gain (Q28 path)
+        pcm = pcm_bytes_full_scale(F, 24, 14)
+        set_preamp(12.0)
+        set_master(0.0)
+        p["host_vol_mul"] = api.host_volume(-256)[0]
+        p["leveller_enabled"] = 0
+        m["outputs"][n_out - 1]["gain_db"] = np.float32(30.0)
+        m["outputs"][n_out - 1]["gain_linear"] = np.float32(10.0 ** (30.0 / 20.0))
+        for side in range(2):
+            m["crosspoints"][side, n_out - 1]["gain_linear"] = np.float32(1.0)
+    elif case == "host_muted":
+        p["host_mute"] = 1
+    elif case == "everything_off":
+        for k in ("loudness_enabled", "crossfeed_enabled", "leveller_enabled"):
+            p[k] = 0
+        p["bypass_master_eq"] = 1
+        for o in range(n_out):
+            m["outputs"][o]["enabled"] = 1 if o == 1 else 0
+            m["outputs"][o]["delay_samples"] = 0
+        bq[0]["bypass"] = 1
+    elif case == "sub_only":
+        for o in range(n_out - 1):
+            m["outputs"][o]["enabled"] = 0
+    else:
+        raise ValueError(case)
+    return p, bq[0], pcm, bit_depth

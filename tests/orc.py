@@ -70,6 +70,8 @@ class Oracle:
         L.orc_loud_table_f32.argtypes = [_vp, C.c_float, C.c_float, C.c_float]
         L.orc_loud_table_q28.argtypes = [_vp, C.c_float, C.c_float, C.c_float]
         L.orc_pdm_modulate.argtypes = [_vp, C.c_int32, _vp]
+        L.orc_mute_envelope.restype = C.c_float
+        L.orc_mute_envelope.argtypes = [_vp, _vp, _vp, _u32, _u32]
 
     # -- knobs -------------------------------------------------------------
     def set_x86_cvt(self, on):
@@ -277,7 +279,9 @@ class OrcChainF32(C.Structure):
                 ("channel_bypassed", C.c_uint8 * 11), ("pad2", C.c_uint8), ("filters", (OrcBiquadF32 * 12) * 11), ("loud", OrcLoudF32 * 2),
                 ("loud_state", (OrcSvfState * 2) * 2), ("xfeed", OrcXfeedF32), ("levc", OrcLevCoeffs), ("levs", OrcLevStateF32),
                 ("delay_lines", (C.c_float * 4096) * 9), ("delay_widx", C.c_uint32), ("pdm", OrcPdm), ("peaks", C.c_uint16 * 11),
-                ("clip_flags", C.c_uint16)]
+                ("clip_flags", C.c_uint16),
+                ("mute_env_on", C.c_uint8), ("preset_loading", C.c_uint8), ("pad3", C.c_uint8 * 2), ("preset_mute_counter", C.c_uint32),
+                ("preset_mute_smooth_gain", C.c_float), ("sample_rate_hz", C.c_uint32)]
 
 
 def make_orc_chain(oracle, params, biquads):
@@ -362,7 +366,9 @@ class OrcChainQ28(C.Structure):
                 ("channel_bypassed", C.c_uint8 * 11), ("pad2", C.c_uint8), ("filters", (OrcBiquadQ28 * 12) * 11), ("loud", OrcLoudQ28 * 2),
                 ("loud_state", (OrcBiquadQ28 * 2) * 2), ("xfeed", OrcXfeedQ28), ("levc", OrcLevCoeffs), ("levs", OrcLevStateQ28),
                 ("delay_lines", (C.c_int32 * 4096) * 9), ("delay_widx", C.c_uint32), ("pdm", OrcPdm), ("peaks", C.c_uint16 * 11),
-                ("clip_flags", C.c_uint16)]
+                ("clip_flags", C.c_uint16),
+                ("mute_env_on", C.c_uint8), ("preset_loading", C.c_uint8), ("pad3", C.c_uint8 * 2), ("preset_mute_counter", C.c_uint32),
+                ("preset_mute_smooth_gain", C.c_float), ("sample_rate_hz", C.c_uint32)]
 
 
 def make_orc_chain_q28(oracle, params, biquads):
@@ -418,3 +424,82 @@ def orc_chain_run_q28(oracle, chain, pcm_bytes, bit_depth, n_packets, fpp):
         oracle.lib.orc_q28_chain_packet(C.addressof(chain), data.ctypes.data + p * fpp * bpf, fpp * bpf, bit_depth,
                                         spdif.ctypes.data + p * fpp * 8, F * 2, pdm.ctypes.data + p * fpp * 32)
     return spdif, pdm
+
+
+def arm_mute_envelope(chain, fs, loading=True, counter=None, smooth_gain=1.0):
+    """Puts one oracle instance into envelope mode the way the firmware arms a preset mute
+    (flash_storage.c:272-276, 347-348: counter = max(512, ceil(fs * 10 ms)), preset_loading = true)."""
+    chain.mute_env_on = 1
+    chain.sample_rate_hz = int(fs)
+    chain.preset_loading = 1 if loading else 0
+    if counter is None:
+        counter = max(512, (int(fs) * 10 + 999) // 1000)
+    chain.preset_mute_counter = int(counter)
+    chain.preset_mute_smooth_gain = float(smooth_gain)
+
+
+class RefChain:
+    """The reference's own process_audio_packet() (usb_audio.c, compiled unmodified by oracle/ref_chain_shim.c)."""
+
+    NAMES = {"f32s": "libdspi_ref_chain_rp2350_strict.so", "f32f": "libdspi_ref_chain_rp2350_fused.so",
+             "q28": "libdspi_ref_chain_rp2040.so"}
+
+    @staticmethod
+    def available():
+        return all(os.path.exists(os.path.join(ORACLE_DIR, "_ref", n)) for n in RefChain.NAMES.values())
+
+    def __init__(self, flavour):
+        self.flavour = flavour
+        self.q28 = flavour == "q28"
+        self.lib = L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", RefChain.NAMES[flavour]))
+        L.ref_chain_sizeof.restype = C.c_size_t
+        L.ref_chain_sizeof.argtypes = [C.c_int]
+        L.ref_chain_packet.restype = _u32
+        L.ref_chain_packet.argtypes = [_vp, _u32, _vp, _u32, _u32, _vp, _u32, _vp, _vp]
+        L.ref_host_vol_mul.restype = C.c_int16
+        L.ref_host_vol_mul.argtypes = [C.c_int16, _vp]
+        L.ref_preamp.argtypes = [C.c_float, _vp, _vp]
+        L.ref_master_volume.argtypes = [C.c_float, _vp, _vp]
+        assert L.ref_chain_sizeof(0) == C.sizeof(OrcChainQ28 if self.q28 else OrcChainF32)
+        self.n_pairs = int(L.ref_chain_sizeof(4))
+
+    def run(self, chain, fs, pcm_bytes, bit_depth, n_packets, fpp):
+        """n_packets packets through the reference; returns (spdif [pairs, F, 2], sub_q28 [n pushed])."""
+        F = n_packets * fpp
+        bpf = 6 if bit_depth == 24 else 4
+        spdif = np.zeros((self.n_pairs, F, 2), np.int32)
+        sub = np.zeros(F, np.int32)
+        got = C.c_uint32()
+        data = np.ascontiguousarray(pcm_bytes)
+        tot = 0
+        for p in range(n_packets):
+            n = self.lib.ref_chain_packet(C.addressof(chain), int(fs), data.ctypes.data + p * fpp * bpf, fpp * bpf, bit_depth,
+                                          spdif.ctypes.data + p * fpp * 8, F * 2, sub.ctypes.data + tot * 4, C.byref(got))
+            assert n == fpp, f"reference returned {n:#x}"
+            tot += got.value
+        return spdif, sub[:tot]
+
+
+class RefPdm:
+    """The reference's own delta-sigma loop (pdm_generator.c, compiled unmodified by oracle/ref_pdm_shim.c)."""
+
+    PATH = os.path.join(ORACLE_DIR, "_ref", "libdspi_ref_pdm.so")
+
+    @staticmethod
+    def available():
+        return os.path.exists(RefPdm.PATH)
+
+    def __init__(self):
+        self.lib = L = C.CDLL(RefPdm.PATH)
+        L.ref_pdm_run.restype = _u32
+        L.ref_pdm_run.argtypes = [_vp, _u32, _vp, _vp, _vp]
+
+    def run(self, samples_q28, seed=123456789):
+        """One stream from the restart state; returns (words [n, 8], rng state after)."""
+        x = np.ascontiguousarray(samples_q28, np.int32)
+        out = np.zeros((len(x), 8), np.uint32)
+        rng = np.array([seed], np.uint32)
+        cnt = np.zeros(4, np.uint32)
+        nw = self.lib.ref_pdm_run(x.ctypes.data, len(x), rng.ctypes.data, out.ctypes.data, cnt.ctypes.data)
+        assert nw == 8 * len(x) and not cnt.any(), (nw, cnt)
+        return out, int(rng[0])
