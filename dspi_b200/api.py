@@ -35,6 +35,7 @@ SYMBOLS = [
     "dspi_bulk_state_defaults", "dspi_bulk_params_apply", "dspi_bulk_params_collect", "dspi_bulk_state_to_chain_f32", "dspi_bulk_state_to_chain_q28",
     "dspi_preset_slot_size", "dspi_crc32", "dspi_preset_slot_apply", "dspi_preset_slot_collect",
     "dspi_preamp", "dspi_master_volume", "dspi_preset_mute_arm", "dspi_preset_mute_step",
+    "dspi_chain_set_preset_mute", "dspi_chain_get_preset_mute", "dspi_chainq_set_preset_mute", "dspi_chainq_get_preset_mute",
 ]
 
 
@@ -119,6 +120,9 @@ def lib():
         h.dspi_preset_mute_arm.argtypes = [vp, u32]
         h.dspi_preset_mute_step.argtypes = [vp, u32, u32]
         h.dspi_preset_mute_step.restype = C.c_float
+        for pre in ("dspi_chain", "dspi_chainq"):
+            getattr(h, pre + "_set_preset_mute").argtypes = [vp, u32, u32, vp, u32]
+            getattr(h, pre + "_get_preset_mute").argtypes = [vp, u32, u32, vp]
         h.dspi_host_alloc.argtypes = [C.c_size_t]
         h.dspi_host_alloc.restype = vp
         h.dspi_host_free.argtypes = [vp]
@@ -244,6 +248,7 @@ class EqEngine:
 
 class ChainEngine:
     """Many independent DSPi device instances, whole signal chain (``dspi_chain_*``)."""
+    _PRE = "dspi_chain"
 
     def __init__(self, arith, n_instances, max_frames, n_bands=L.NUM_BANDS, device=0):
         self.arith = ARITH[arith] if isinstance(arith, str) else int(arith)
@@ -298,6 +303,21 @@ class ChainEngine:
     def state_import(self, blob):
         b = np.ascontiguousarray(blob, np.uint8)
         _check(getattr(lib(), "dspi_chain_state_import")(self._h, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size)))
+
+    def set_preset_mute(self, states, fs, inst0=0, n=None):
+        """Envelope mode for instances [inst0, inst0+n): ``states`` PRESET_MUTE [n], or None to leave envelope mode."""
+        if states is None:
+            n = self.n_instances - inst0 if n is None else n
+            _check(getattr(lib(), self._PRE + "_set_preset_mute")(self._h, int(inst0), int(n), None, int(fs)))
+            return
+        st = np.ascontiguousarray(states, L.PRESET_MUTE)
+        _check(getattr(lib(), self._PRE + "_set_preset_mute")(self._h, int(inst0), int(st.shape[0]), st.ctypes.data_as(C.c_void_p), int(fs)))
+
+    def get_preset_mute(self, n=None, inst0=0):
+        n = self.n_instances - inst0 if n is None else n
+        out = np.zeros(n, L.PRESET_MUTE)
+        _check(getattr(lib(), self._PRE + "_get_preset_mute")(self._h, int(inst0), int(n), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def reset_state(self):
         _check(lib().dspi_chain_reset_state(self._h))
@@ -479,6 +499,7 @@ def master_volume(db):
 
 class ChainEngineQ28:
     """Many independent RP2040-shape instances (2 in -> 5 out), Q28 arithmetic (``dspi_chainq_*``)."""
+    _PRE = "dspi_chainq"
 
     def __init__(self, n_instances, max_frames, n_bands=L.NUM_BANDS, device=0):
         self.n_instances, self.max_frames, self.device = int(n_instances), int(max_frames), int(device)
@@ -531,6 +552,21 @@ class ChainEngineQ28:
     def state_import(self, blob):
         b = np.ascontiguousarray(blob, np.uint8)
         _check(getattr(lib(), "dspi_chainq_state_import")(self._h, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size)))
+
+    def set_preset_mute(self, states, fs, inst0=0, n=None):
+        """Envelope mode for instances [inst0, inst0+n): ``states`` PRESET_MUTE [n], or None to leave envelope mode."""
+        if states is None:
+            n = self.n_instances - inst0 if n is None else n
+            _check(getattr(lib(), self._PRE + "_set_preset_mute")(self._h, int(inst0), int(n), None, int(fs)))
+            return
+        st = np.ascontiguousarray(states, L.PRESET_MUTE)
+        _check(getattr(lib(), self._PRE + "_set_preset_mute")(self._h, int(inst0), int(st.shape[0]), st.ctypes.data_as(C.c_void_p), int(fs)))
+
+    def get_preset_mute(self, n=None, inst0=0):
+        n = self.n_instances - inst0 if n is None else n
+        out = np.zeros(n, L.PRESET_MUTE)
+        _check(getattr(lib(), self._PRE + "_get_preset_mute")(self._h, int(inst0), int(n), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def reset_state(self):
         _check(lib().dspi_chainq_reset_state(self._h))

@@ -68,6 +68,10 @@ struct ChainDev {
     float *orow;                                  // [9 N_pad][ldF] output rows, row = o * N_pad + inst
     int32_t *subq;                                // [N_pad][ldF] Q28 sub samples for the modulator
     uint8_t *skip_m, *skip_o;                     // [2 N_pad], [9 N_pad]: rows whose EQ is frozen (K1 skip mask)
+    // preset-mute envelope (usb_audio.c:456-498): per-instance state and the per-packet volume it produces
+    uint32_t *env;                                // [5][N_pad] loading, counter, smooth gain (float bits), sample rate, envelope mode on
+    float *vol_base, *vol_master, *o_glin;        // [N_pad] host volume (:569), [N_pad] master volume, [9][N_pad] outputs[o].gain_linear
+    float *vmm;                                   // [packets of the call][N_pad] vol_mul_master (:571) of envelope-mode instances
 };
 
 // a*b + c, c - a*b in the flavour's rounding (scalar: negation is free)
@@ -427,6 +431,39 @@ chain_mix_kernel(ChainDev d, uint32_t f_begin, uint32_t f_end)
 // ---------------------------------------------------------------------------------------------
 // outputs after the EQ: gain (:885-894), delay (:898-912), peaks (:914-923), 24-bit / Q28 (:925-959)
 // ---------------------------------------------------------------------------------------------
+// update_preset_mute_envelope() (usb_audio.c:466-498) for every packet of the call, one instance per thread, and the
+// volume chain of :569-571 that depends on it: vmm[p] = (vol_base * g_p) * master_volume_linear.  Same operations, same
+// order as dspi_preset_mute_step() on the host.
+__global__ void chain_env_kernel(ChainDev d, uint32_t n_packets, uint32_t fpp)
+{
+    const uint32_t inst = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t Np = d.N_pad;
+    if (inst >= d.N || !d.env[4 * Np + inst]) return;
+    uint32_t loading = d.env[0 * Np + inst], counter = d.env[1 * Np + inst];
+    float g = __uint_as_float(d.env[2 * Np + inst]);
+    const uint32_t fs = d.env[3 * Np + inst];
+    unsigned long long ts = ((unsigned long long)fs * 8ull + 999ull) / 1000ull;          // :459-464
+    if (ts < 1ull) ts = 1ull;
+    if (ts > 0xFFFFFFFFull) ts = 0xFFFFFFFFull;
+    float step = __fdiv_rn((float)fpp, (float)(uint32_t)ts);                             // :486
+    if (step > 1.0f) step = 1.0f;
+    const float vol_base = d.vol_base[inst], master = d.vol_master[inst];
+    for (uint32_t p = 0; p < n_packets; p++) {
+        const bool active = loading != 0;                                                // :469
+        if (active) {
+            if (counter > fpp) counter -= fpp;
+            else { counter = 0; loading = 0; }
+        }
+        const float target = active ? 0.0f : 1.0f;
+        if (g < target)      { g = __fadd_rn(g, step);  if (g > target) g = target; }
+        else if (g > target) { g = __fadd_rn(g, -step); if (g < target) g = target; }
+        d.vmm[(size_t)p * Np + inst] = __fmul_rn(__fmul_rn(vol_base, g), master);        // :570-571
+    }
+    d.env[0 * Np + inst] = loading;
+    d.env[1 * Np + inst] = counter;
+    d.env[2 * Np + inst] = __float_as_uint(g);
+}
+
 // post-gain sample of output row `o` (what the delay line stores)
 __device__ __forceinline__ float out_gain(float v, bool enabled, float gain)
 {
@@ -438,14 +475,17 @@ __device__ __forceinline__ float out_gain(float v, bool enabled, float gain)
 }
 
 struct OutCfg {
-    bool enabled, pair_off, delay_on;
-    float gain;
+    bool enabled, pair_off, delay_on, mute;
+    float gain;                        // constant gain of the call (no envelope)
+    float glin;                        // outputs[o].gain_linear
+    const float *vmm;                  // envelope mode: vol_mul_master per packet, stride N_pad; else nullptr
+    uint32_t fpp, Np;
     uint32_t dl;                       // delay & (MAX - 1): MAX aliases to 0 (SURVEY a-10)
     const float *row;                  // orow row of this (output, instance)
     const float *ring;
 };
 
-__device__ __forceinline__ OutCfg out_cfg(const ChainDev &d, uint32_t o, uint32_t inst, bool any_delay)
+__device__ __forceinline__ OutCfg out_cfg(const ChainDev &d, uint32_t o, uint32_t inst, bool any_delay, uint32_t fpp)
 {
     OutCfg c;
     const uint32_t Np = d.N_pad;
@@ -453,7 +493,12 @@ __device__ __forceinline__ OutCfg out_cfg(const ChainDev &d, uint32_t o, uint32_
     const int32_t dly = d.o_dly[o * Np + inst];
     c.enabled = of & O_ENABLED;
     c.pair_off = of & O_PAIR_OFF;
+    c.mute = of & O_MUTE;
     c.gain = d.o_gain[o * Np + inst];
+    c.glin = d.o_glin[o * Np + inst];
+    c.vmm = d.env[4 * Np + inst] ? d.vmm + inst : nullptr;
+    c.fpp = fpp;
+    c.Np = Np;
     c.delay_on = any_delay && dly > 0;                                       // usb_audio.c:898-901
     c.dl = (uint32_t)dly & (kMaxDelay - 1);
     c.row = d.orow + ((size_t)o * Np + inst) * d.ldF;
@@ -461,13 +506,20 @@ __device__ __forceinline__ OutCfg out_cfg(const ChainDev &d, uint32_t o, uint32_
     return c;
 }
 
+// output gain in force at frame T of the call (usb_audio.c:886-887): constant, or following the envelope packet by packet
+__device__ __forceinline__ float gain_at(const OutCfg &c, uint32_t T)
+{
+    if (!c.vmm) return c.gain;
+    return c.mute ? 0.0f : __fmul_rn(c.glin, c.vmm[(size_t)(T / c.fpp) * c.Np]);
+}
+
 // the sample output `c` emits at frame T of this call (T counted from the start of the call):
 // write-then-read per sample (:902-909) means frame T emits the post-gain sample of frame T - dl;
 // inside the call that sample is still in the output rows, before it only the ring has it
 __device__ __forceinline__ float out_sample(const OutCfg &c, uint32_t T, uint32_t widx0)
 {
-    if (!c.delay_on) return out_gain(c.row[T], c.enabled, c.gain);
-    if (T >= c.dl) return out_gain(c.row[T - c.dl], c.enabled, c.gain);
+    if (!c.delay_on) return out_gain(c.row[T], c.enabled, gain_at(c, T));
+    if (T >= c.dl) return out_gain(c.row[T - c.dl], c.enabled, gain_at(c, T - c.dl));
     return c.ring[(widx0 + T - c.dl) & (kMaxDelay - 1)];
 }
 
@@ -497,7 +549,7 @@ chain_outpost_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, 
         for (int k = 0; k <= 4; k++) {                                        // four S/PDIF pairs, then the sub alone
             const bool is_sub = k == 4;
             const uint32_t oa = 2 * k, ob = is_sub ? oa : oa + 1;
-            const OutCfg ca = out_cfg(d, oa, inst, any_delay), cb = out_cfg(d, ob, inst, any_delay);
+            const OutCfg ca = out_cfg(d, oa, inst, any_delay, fpp), cb = out_cfg(d, ob, inst, any_delay, fpp);
             float pka = 0.0f, pkb = 0.0f;
             constexpr int kB = 4;                                            // independent loads in flight per lane
             for (uint32_t tb = lane; tb < fpp; tb += 32 * kB) {
@@ -556,11 +608,11 @@ chain_ring_kernel(ChainDev d, uint32_t F, uint32_t fpp)
         const uint32_t inst = (uint32_t)(u / kOuts), o = (uint32_t)(u % kOuts);
         const bool any_delay = d.flags[inst] & F_ANY_DELAY;
         const uint32_t widx0 = d.widx_in[inst];
-        const OutCfg c = out_cfg(d, o, inst, any_delay);
+        const OutCfg c = out_cfg(d, o, inst, any_delay, fpp);
         if (c.delay_on) {                                                    // outputs without delay never touch their ring
             float *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;
             for (uint32_t T = (F > (uint32_t)kMaxDelay ? F - kMaxDelay : 0u) + lane; T < F; T += 32)
-                ring[(widx0 + T) & (kMaxDelay - 1)] = out_gain(c.row[T], c.enabled, c.gain);
+                ring[(widx0 + T) & (kMaxDelay - 1)] = out_gain(c.row[T], c.enabled, gain_at(c, T));
         }
         if (o == 0 && lane == 0) d.widx_out[inst] = any_delay ? (widx0 + F) & (kMaxDelay - 1) : widx0;   // :911, once per packet
     }
@@ -639,6 +691,8 @@ struct dspi_chain {
     int32_t *d_spdif; size_t spdif_bytes;
     uint32_t *d_pdmout; size_t pdmout_bytes;
     dspi_status *d_status;
+    uint32_t env_instances;          // instances in envelope mode (0: the envelope kernel and its table are not needed)
+    uint32_t vmm_packets;            // capacity of d.vmm in packets
 };
 
 namespace {
@@ -694,6 +748,18 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
     // i+1 overlap the output stages of slice i and the modulator of slice i-1.
     dspi::ChainStreams &st = c->st;
     const uint32_t n_slices = n_packets < (uint32_t)dspi::ChainStreams::kMaxSlices ? n_packets : (uint32_t)dspi::ChainStreams::kMaxSlices;
+    if (c->env_instances) {                                                  // preset-mute envelope: this call's per-packet volumes
+        if (c->vmm_packets < n_packets) {
+            CU_OK(cudaStreamSynchronize(c->stream));
+            if (c->d.vmm) CU_OK(cudaFree(c->d.vmm));
+            c->d.vmm = nullptr; c->vmm_packets = 0;
+            CU_OK(cudaMalloc((void **)&c->d.vmm, (size_t)n_packets * c->d.N_pad * sizeof(float)));
+            c->vmm_packets = n_packets;
+        }
+        dspi::chain_env_kernel<<<(c->d.N + 127) / 128, 128, 0, c->stream>>>(c->d, n_packets, fpp);
+        CU_OK(cudaGetLastError());
+        c->launches++;
+    }
     const ChainDev d = c->d;
     const uint32_t n_sms = 148;
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
@@ -766,6 +832,7 @@ int dspi_chain_destroy(dspi_chain *c)
     if (c->d_pcm) cudaFree(c->d_pcm);
     if (c->d_spdif) cudaFree(c->d_spdif);
     if (c->d_pdmout) cudaFree(c->d_pdmout);
+    if (c->d.vmm) cudaFree(c->d.vmm);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     cudaGetLastError();
@@ -793,6 +860,7 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     c->eq_m = c->eq_o = nullptr;
     c->d_aos = nullptr; c->launches = 0; c->d_pcm = nullptr; c->pcm_bytes = 0; c->d_spdif = nullptr; c->spdif_bytes = 0;
     c->d_pdmout = nullptr; c->pdmout_bytes = 0; c->d_status = nullptr;
+    c->env_instances = 0; c->vmm_packets = 0;
     c->desc = *desc;
     ChainDev &d = c->d;
     memset(&d, 0, sizeof(d));
@@ -843,6 +911,10 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     TRY(dev_alloc(c, &d.skip_m, 2 * Np));
     TRY(dev_alloc(c, &d.skip_o, dspi::kOuts * Np));
     TRY(dev_alloc(c, &c->d_status, Np));
+    TRY(dev_alloc(c, &d.env, 5 * Np));
+    TRY(dev_alloc(c, &d.vol_base, Np));
+    TRY(dev_alloc(c, &d.vol_master, Np));
+    TRY(dev_alloc(c, &d.o_glin, dspi::kOuts * Np));
     TRY(init_states(c));
 #undef TRY
     if (e != cudaSuccess) {
@@ -870,13 +942,18 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
     CU_OK(cudaSetDevice(c->desc.device));
     const ChainDev &d = c->d;
     const size_t Np = d.N_pad;
-    std::vector<float> preamp(2 * n), loud_c(12 * n), xf(7 * n), lev_c(9 * n), gl(9 * n), gr(9 * n), gain(9 * n);
+    std::vector<float> preamp(2 * n), loud_c(12 * n), xf(7 * n), lev_c(9 * n), gl(9 * n), gr(9 * n), gain(9 * n), glin(9 * n), vbase(n), vmaster(n);
     std::vector<uint8_t> flags(n), loud_byp(n), oflags(9 * n), skip_m(2 * n), skip_o(9 * n);
     std::vector<int32_t> dly(9 * n);
+    std::vector<float> xf_cur(7 * n);
+    CU_OK(cudaMemcpy2DAsync(xf_cur.data(), (size_t)n * 4, d.xf + inst0, Np * 4, (size_t)n * 4, 7, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
     for (uint32_t i = 0; i < n; i++) {
         const dspi_chain_params_f32 &p = params[i];
         // usb_audio.c:569-571
         float vol_mul = p.host_mute ? 0.0f : (float)p.host_vol_mul * (1.0f / 32768.0f);
+        vbase[i] = vol_mul;
+        vmaster[i] = p.master_volume_linear;
         vol_mul *= p.preset_mute_gain;
         const float vol_mul_master = vol_mul * p.master_volume_linear;
         preamp[0 * n + i] = p.preamp_linear[0];
@@ -891,6 +968,7 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
             gl[o * n + i] = a;
             gr[o * n + i] = b;
             gain[o * n + i] = oc.mute ? 0.0f : oc.gain_linear * vol_mul_master;    // :886-887
+            glin[o * n + i] = oc.gain_linear;
             uint8_t f = (oc.enabled ? dspi::O_ENABLED : 0) | (oc.mute ? dspi::O_MUTE : 0);
             if (o < dspi::kOuts - 1) {
                 const int partner = o ^ 1;
@@ -916,7 +994,14 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
         }
         const float xv[7] = { p.crossfeed.lp_a0, p.crossfeed.lp_b1, p.crossfeed.lp_state_L, p.crossfeed.lp_state_R,
                               p.crossfeed.ap_a, p.crossfeed.ap_state_L, p.crossfeed.ap_state_R };
-        for (int k = 0; k < 7; k++) xf[k * n + i] = xv[k];
+        // crossfeed_compute_coefficients() is the only writer of crossfeed_state in the firmware and it clears the filter
+        // state (crossfeed.c:35-127); a volume / mute / matrix update never touches it.  So the record's state rows are
+        // taken only when its coefficients differ from the ones in force; otherwise the running state is kept.
+        const bool xf_same = xv[0] == xf_cur[0 * n + i] && xv[1] == xf_cur[1 * n + i] && xv[4] == xf_cur[4 * n + i];
+        for (int k = 0; k < 7; k++) {
+            const bool is_state = k == 2 || k == 3 || k == 5 || k == 6;
+            xf[k * n + i] = (is_state && xf_same) ? xf_cur[k * n + i] : xv[k];
+        }
         const float *lv = &p.leveller.alpha_rms;
         for (int k = 0; k < 9; k++) lev_c[k * n + i] = lv[k];
     }
@@ -933,6 +1018,9 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
     CU_OK(put(d.o_gl, gl.data(), 9, 4));
     CU_OK(put(d.o_gr, gr.data(), 9, 4));
     CU_OK(put(d.o_gain, gain.data(), 9, 4));
+    CU_OK(put(d.o_glin, glin.data(), 9, 4));
+    CU_OK(put(d.vol_base, vbase.data(), 1, 4));
+    CU_OK(put(d.vol_master, vmaster.data(), 1, 4));
     CU_OK(put(d.o_flags, oflags.data(), 9, 1));
     CU_OK(put(d.o_dly, dly.data(), 9, 4));
     CU_OK(put(d.skip_m, skip_m.data(), 2, 1));
@@ -941,6 +1029,53 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
     int rc = dspi::eq_set_skip(c->eq_m, d.skip_m, c->stream);
     if (rc == DSPI_OK) rc = dspi::eq_set_skip(c->eq_o, d.skip_o, c->stream);
     return rc;
+}
+
+/* preset-mute envelope of instances [inst0, inst0+n): states == NULL leaves envelope mode (the constant
+ * preset_mute_gain of dspi_chain_set_params applies again) */
+int dspi_chain_set_preset_mute(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_preset_mute *states, uint32_t sample_rate_hz)
+{
+    if (!c) return fail(DSPI_EINVAL, "null argument");
+    if ((uint64_t)inst0 + n > c->desc.n_instances) return fail(DSPI_ERANGE, "instances [%u, %u) outside engine of %u", inst0, inst0 + n, c->desc.n_instances);
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(c->desc.device));
+    const size_t Np = c->d.N_pad;
+    std::vector<uint32_t> cur((size_t)n), rows((size_t)5 * n, 0u);
+    CU_OK(cudaMemcpyAsync(cur.data(), c->d.env + 4 * Np + inst0, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; i++) {
+        if (cur[i]) c->env_instances--;
+        if (states) {
+            rows[0 * n + i] = states[i].loading ? 1u : 0u;
+            rows[1 * n + i] = states[i].counter;
+            memcpy(&rows[2 * n + i], &states[i].smooth_gain, 4);
+            rows[3 * n + i] = sample_rate_hz;
+            rows[4 * n + i] = 1u;
+            c->env_instances++;
+        }
+    }
+    CU_OK(cudaMemcpy2DAsync(c->d.env + inst0, Np * 4, rows.data(), (size_t)n * 4, (size_t)n * 4, 5, cudaMemcpyHostToDevice, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+    return DSPI_OK;
+}
+
+int dspi_chain_get_preset_mute(dspi_chain *c, uint32_t inst0, uint32_t n, dspi_preset_mute *states)
+{
+    if (!c || !states) return fail(DSPI_EINVAL, "null argument");
+    if ((uint64_t)inst0 + n > c->desc.n_instances) return fail(DSPI_ERANGE, "instances [%u, %u) outside engine of %u", inst0, inst0 + n, c->desc.n_instances);
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(c->desc.device));
+    const size_t Np = c->d.N_pad;
+    std::vector<uint32_t> rows((size_t)3 * n);
+    CU_OK(cudaMemcpy2DAsync(rows.data(), (size_t)n * 4, c->d.env + inst0, Np * 4, (size_t)n * 4, 3, cudaMemcpyDeviceToHost, c->stream));
+    CU_OK(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; i++) {
+        memset(&states[i], 0, sizeof(states[i]));
+        states[i].loading = (uint8_t)rows[0 * n + i];
+        states[i].counter = rows[1 * n + i];
+        memcpy(&states[i].smooth_gain, &rows[2 * n + i], 4);
+    }
+    return DSPI_OK;
 }
 
 int dspi_chain_upload_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_biquad_f32 *biquads)
@@ -970,6 +1105,10 @@ int dspi_chain_set_eq_params_device(dspi_chain *c, uint32_t inst0, uint32_t n, d
     if (!c || !recipes) return fail(DSPI_EINVAL, "null argument");
     if ((uint64_t)inst0 + n > c->desc.n_instances) return fail(DSPI_ERANGE, "instances [%u, %u) outside engine of %u", inst0, inst0 + n, c->desc.n_instances);
     if (n == 0) return DSPI_OK;
+    // the sub-engines generate and pack on their own streams: everything issued on the engine stream so far (an
+    // asynchronous process_device in particular) must have finished reading the coefficient stores first
+    CU_OK(cudaSetDevice(c->desc.device));
+    CU_OK(cudaStreamSynchronize(c->stream));
     const uint32_t Np = c->d.N_pad;
     std::vector<dspi_eq_param> tmp((size_t)n * DSPI_MAX_BANDS);
     for (int role = 0; role < dspi::kRoles; role++) {               // filter_recipes[role][band] of every instance -> one engine range per role
@@ -1036,7 +1175,7 @@ int dspi_chain_process_host(dspi_chain *c, const void *pcm, uint32_t bit_depth, 
     const size_t in_bytes = N * F * (bit_depth == 24 ? 6 : 4), sp_bytes = N * 4 * F * 2 * 4, pd_bytes = N * F * 8 * 4;
     if (in_bytes > c->pcm_bytes) { if (c->d_pcm) cudaFree(c->d_pcm); c->d_pcm = nullptr; c->pcm_bytes = 0; CU_OK(cudaMalloc(&c->d_pcm, in_bytes)); c->pcm_bytes = in_bytes; }
     if (spdif_out && sp_bytes > c->spdif_bytes) { if (c->d_spdif) cudaFree(c->d_spdif); c->d_spdif = nullptr; c->spdif_bytes = 0; CU_OK(cudaMalloc((void **)&c->d_spdif, sp_bytes)); c->spdif_bytes = sp_bytes; }
-    if (pdm_out && pd_bytes > c->pdmout_bytes) { if (c->d_pdmout) cudaFree(c->d_pdmout); c->d_pdmout = nullptr; c->pdmout_bytes = 0; CU_OK(cudaMalloc((void **)&c->d_pdmout, pd_bytes)); c->pdmout_bytes = pd_bytes; }
+    if (pdm_out && pd_bytes > c->pdmout_bytes) { if (c->d_pdmout) cudaFree(c->d_pdmout); c->d_pdmout = nullptr; c->pdmout_bytes = 0; CU_OK(cudaMalloc((void **)&c->d_pdmout, pd_bytes)); c->pdmout_bytes = pd_bytes; CU_OK(cudaMemsetAsync(c->d_pdmout, 0, pd_bytes, c->stream)); }
     CU_OK(cudaMemcpyAsync(c->d_pcm, pcm, in_bytes, cudaMemcpyHostToDevice, c->stream));
     rc = dspi_chain_process_device(c, c->d_pcm, bit_depth, n_packets, fpp, spdif_out ? c->d_spdif : nullptr, pdm_out ? c->d_pdmout : nullptr,
                                    status ? c->d_status : nullptr);
@@ -1063,6 +1202,7 @@ static void state_sections(dspi_chain *c, std::vector<std::pair<void *, size_t>>
     v.push_back({ c->d.pdm, 9 * Np * 4 });
     v.push_back({ c->d.peaks, (size_t)dspi::kRoles * Np * 2 });
     v.push_back({ c->d.clip, Np * 2 });
+    v.push_back({ c->d.env, 5 * Np * 4 });                                 // preset-mute envelope state and mode
     dspi::eq_state_sections(c->eq_m, v);
     dspi::eq_state_sections(c->eq_o, v);
 }
@@ -1122,7 +1262,11 @@ int dspi_chain_state_import(dspi_chain *c, const void *blob, size_t len)
     int rc = dspi::eq_state_imported(c->eq_m, c->stream);
     if (rc == DSPI_OK) rc = dspi::eq_state_imported(c->eq_o, c->stream);
     if (rc) return rc;
+    std::vector<uint32_t> on(c->d.N);
+    CU_OK(cudaMemcpyAsync(on.data(), c->d.env + (size_t)4 * c->d.N_pad, (size_t)c->d.N * 4, cudaMemcpyDeviceToHost, c->stream));
     CU_OK(cudaStreamSynchronize(c->stream));
+    c->env_instances = 0;
+    for (uint32_t v : on) c->env_instances += v ? 1u : 0u;
     return DSPI_OK;
 }
 

@@ -466,6 +466,9 @@ void eq_state_sections(dspi_eq *e, std::vector<std::pair<void *, size_t>> &out)
     const size_t coef_bytes = q28 ? (size_t)e->n_groups * DSPI_MAX_BANDS * 20 * 32 * 4 : (size_t)e->c_pad * DSPI_MAX_BANDS * 8 * 4;
     out.push_back({ e->d_coef, coef_bytes });
     if (e->d_modes) out.push_back({ e->d_modes, (size_t)e->c_pad * 8 });
+    // the reference-layout mirror too: download / device-side coefficient edits start from it (its coefficients,
+    // bypass and topology fields are not recoverable from the packed store alone)
+    out.push_back({ e->d_aos, (size_t)e->c_pad * DSPI_MAX_BANDS * e->aos_elem });
 }
 
 // after the sections were overwritten: effective topology words and the kernel choice must be re-derived

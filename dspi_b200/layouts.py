@@ -155,3 +155,7 @@ BULK_STATE = np.dtype({
                 (OUTPUT, (WIRE_MAX_OUTPUTS,)), (EQ_PARAM, (WIRE_MAX_CHANNELS, MAX_BANDS))],
     "offsets": [0, 4, 12, 20, 28, 32, 36, 40, 41, 44, 48, 52, 64, 88, 100, 112, 124, 128, 172, 388, 568],
     "itemsize": 2680})
+
+# dspi_preset_mute (include/dspi_b200.h): state of update_preset_mute_envelope(), usb_audio.c:456-498
+PRESET_MUTE = np.dtype([("loading", "u1"), ("reserved", "u1", (3,)), ("counter", "<u4"), ("smooth_gain", "<f4")])
+assert PRESET_MUTE.itemsize == 12

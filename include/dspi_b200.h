@@ -254,7 +254,10 @@ typedef struct {
 int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc);
 int dspi_chain_destroy(dspi_chain *c);
 /* bulk_params_apply()-style update between packets (bulk_params.c:178-377 + main.c:1126-1162):
- * params[n] for instances [inst0, inst0+n).  Filter, delay-line, leveller and PDM state are kept. */
+ * params[n] for instances [inst0, inst0+n).  Filter, delay-line, leveller and PDM state are kept; so is the crossfeed
+ * filter state unless the record's crossfeed COEFFICIENTS differ from the ones in force - then the record's state rows
+ * are taken, i.e. the zeros crossfeed_compute_coefficients() leaves (crossfeed.c:35-127 is the only place the firmware
+ * resets that state; audio_set_volume and the mute / matrix handlers never do). */
 int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_chain_params_f32 *params);
 /* filters[NUM_CHANNELS][MAX_BANDS] of n instances: biquads[n][11][12] (master L, R, Out1..9) */
 int dspi_chain_upload_biquads(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_biquad_f32 *biquads);
@@ -265,6 +268,14 @@ int dspi_chain_set_eq_params_device(dspi_chain *c, uint32_t inst0, uint32_t n, d
 /* pipeline reset: clears leveller, loudness, delay-line and PDM state (leveller_reset_state(),
  * pdm_processing_loop() restart path); filter state is part of the biquads */
 int dspi_chain_reset_state(dspi_chain *c);
+/* The preset-mute envelope inside the engine (update_preset_mute_envelope(), usb_audio.c:466-498, called once per packet
+ * at :532): states[n] puts instances [inst0, inst0+n) into envelope mode - from then on every packet of every process
+ * call advances the instance's envelope and uses its gain where process_audio_packet() uses preset_mute_gain (:570), so a
+ * fade runs across the packets of one call and across calls.  Arm a mute with dspi_preset_mute_arm() as the firmware's
+ * flash operations do.  states == NULL leaves envelope mode: the constant preset_mute_gain of dspi_chain_set_params
+ * applies again.  _get_ returns the current state (it is part of the state blob too). */
+int dspi_chain_set_preset_mute(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_preset_mute *states, uint32_t sample_rate_hz);
+int dspi_chain_get_preset_mute(dspi_chain *c, uint32_t inst0, uint32_t n, dspi_preset_mute *states);
 /* Checkpoint / resume (the dspi_state_export/import of SURVEY 8 b): everything a later process call depends on besides
  * dspi_chain_set_params' records - filter coefficients and state, loudness / crossfeed / leveller state, look-ahead and
  * delay rings, write index, modulator state, meters.  The blob is private to this library (header + raw arrays) and only
@@ -340,6 +351,8 @@ int dspi_chainq_upload_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, const
 int dspi_chainq_download_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_biquad_q28 *biquads);
 int dspi_chainq_set_eq_params_device(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_eq_param *recipes, float sample_rate);   /* recipes[n][7][12] */
 int dspi_chainq_reset_state(dspi_chainq *c);
+int dspi_chainq_set_preset_mute(dspi_chainq *c, uint32_t inst0, uint32_t n, const dspi_preset_mute *states, uint32_t sample_rate_hz);   /* Q15 use of the gain: usb_audio.c:976-980 */
+int dspi_chainq_get_preset_mute(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_preset_mute *states);
 size_t dspi_chainq_state_size(dspi_chainq *c);
 int dspi_chainq_state_export(dspi_chainq *c, void *blob, size_t cap);
 int dspi_chainq_state_import(dspi_chainq *c, const void *blob, size_t len);

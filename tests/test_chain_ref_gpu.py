@@ -1,0 +1,371 @@
+"""GPU chain against the reference's own compiled code (oracle/_ref travels to the GPU box), the documented quirks,
+the libm-policy deviation bound, the preset-mute envelope inside a call, and the round-1 advisor findings."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from dspi_b200 import api, layouts as L                                                         # noqa: E402
+from tests.chain_cases import QUIRK_CASES, chain_params, chain_params_q28, pcm_bytes, quirk_cases  # noqa: E402
+from tests.orc import (RefChain, RefPdm, arm_mute_envelope, make_orc_chain, make_orc_chain_q28, orc_chain_run,  # noqa: E402
+                       orc_chain_run_q28)
+
+FS = 96000.0
+
+
+def _engine(flavour, N, F):
+    return api.ChainEngineQ28(N, max_frames=F) if flavour == "q28" else api.ChainEngine(flavour, N, max_frames=F)
+
+
+def _orc(oracle, flavour, P, bq):
+    return make_orc_chain_q28(oracle, P, bq) if flavour == "q28" else make_orc_chain(oracle, P, bq)
+
+
+def _orc_run(oracle, flavour, ch, pcm, bit_depth, n_packets, fpp):
+    if flavour == "q28":
+        return orc_chain_run_q28(oracle, ch, pcm, bit_depth, n_packets, fpp)
+    return orc_chain_run(oracle, flavour, ch, pcm, bit_depth, n_packets, fpp)
+
+
+def _params(oracle, flavour, N, seed, **kw):
+    if flavour == "q28":
+        kw.pop("uniform", None)
+        return chain_params_q28(oracle, N, FS, seed, **kw)
+    return chain_params(oracle, N, FS, seed, **kw)
+
+
+# ---- the GPU against usb_audio.c / pdm_generator.c compiled on this host --------------------------------------------
+@pytest.mark.parametrize("bit_depth", [16, 24])
+@pytest.mark.parametrize("flavour", ["f32f", "f32s", "q28"])
+def test_gpu_chain_equals_compiled_reference(oracle, flavour, bit_depth):
+    """No restatement in between: S/PDIF words, PDM bits, meters of the CUDA chain == the reference's own
+    process_audio_packet() + modulator loop.  Leveller off here (its libm is the one policy item, next test)."""
+    if not (RefChain.available() and RefPdm.available()):
+        pytest.skip("oracle/_ref chain builds not present")
+    ref, ref_pdm = RefChain(flavour), RefPdm()
+    N, n_packets, fpp = 24, 8, 96
+    P, bq = _params(oracle, flavour, N, 400, leveller=False)
+    for i in range(N):
+        P[i]["preset_mute_gain"] = 1.0
+    pcm = pcm_bytes(N, n_packets * fpp, bit_depth, 401)
+    sub_o = 4 if flavour == "q28" else 8
+    eng = _engine(flavour, N, n_packets * fpp)
+    try:
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        spdif, pdm, status = eng.process_host(pcm, bit_depth, n_packets, fpp)
+        for i in range(N):
+            ch = _orc(oracle, flavour, P[i], bq[i])
+            ws, sub = ref.run(ch, FS, pcm[i], bit_depth, n_packets, fpp)
+            assert np.array_equal(spdif[i], ws), f"instance {i}: S/PDIF words differ from the compiled reference"
+            if P[i]["matrix"]["outputs"][sub_o]["enabled"]:
+                words, _ = ref_pdm.run(sub)
+                assert np.array_equal(pdm[i], words), f"instance {i}: PDM bits differ from the compiled reference"
+            n_roles = 7 if flavour == "q28" else 11
+            assert list(status[i]["peaks"]) == list(ch.peaks)[:n_roles]
+            assert int(status[i]["clip_flags"]) == int(ch.clip_flags)
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "q28"])
+def test_leveller_libm_policy_deviation_is_bounded(oracle, flavour):
+    """the device evaluates the leveller's per-block log10f / powf in double and rounds once; the compiled
+    reference uses glibc's float routines.  GPU words vs the glibc-flavoured oracle (pinned to oracle/_ref bit for bit):
+    float chain <= 1 LSB of the 24-bit word; Q28 chain <= 1 LSB as long as no Q28 EQ follows the leveller (the
+    truncating Q28 biquads decorrelate their own round-off noise after a 1-LSB change, so behind them the bound is the
+    filters' noise floor, asserted here as < -72 dBFS and reported)."""
+    N, n_packets, fpp = 32, 60, 96
+    P, bq = _params(oracle, flavour, N, 77)
+    for i in range(N):
+        P[i]["leveller_enabled"] = 1
+        P[i]["preset_mute_gain"] = 1.0
+    pcm = pcm_bytes(N, n_packets * fpp, 24, 5)
+    for flat_outputs in ([True, False] if flavour == "q28" else [False]):
+        b = bq.copy()
+        if flat_outputs:
+            b[:, 2:]["bypass"] = 1
+        eng = _engine(flavour, N, n_packets * fpp)
+        try:
+            eng.set_params(P)
+            eng.upload_biquads(b)
+            spdif, _, _ = eng.process_host(pcm, 24, n_packets, fpp)
+        finally:
+            eng.close()
+        oracle.set_libm_f64(0)                                   # glibc float routines == oracle/_ref
+        want = np.stack([_orc_run(oracle, flavour, _orc(oracle, flavour, P[i], b[i]), pcm[i], 24, n_packets, fpp)[0] for i in range(N)])
+        d = np.abs(spdif.astype(np.int64) - want)
+        frac = float((d > 0).mean())
+        print(f"{flavour} flat_outputs={flat_outputs}: max |GPU - glibc reference| = {int(d.max())} LSB24, {frac:.2e} of the words differ")
+        if flavour != "q28" or flat_outputs:
+            assert d.max() <= (1 if flat_outputs else 4) and frac < 5e-3
+        else:
+            assert d.max() < (1 << 23) * 10 ** (-72 / 20) and frac < 5e-2
+
+
+# ---- quirks -----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", QUIRK_CASES)
+@pytest.mark.parametrize("flavour", ["f32f", "f32s", "q28"])
+def test_gpu_chain_quirks(oracle, flavour, case):
+    """0 dB host volume = polarity flip, dly == MAX alias, clip flags that actually set, float -> Q28 saturation for
+    |x| >= 8, mute / disabled pairs - each next to two ordinary instances in the same engine."""
+    n_packets, fpp = 50, 96
+    F = n_packets * fpp
+    Pq, bqq, pcm_q, bit_depth = quirk_cases(oracle, flavour, case, FS, F)
+    P, bq = _params(oracle, flavour, 3, 500)
+    P[1], bq[1] = Pq, bqq
+    for i in range(3):
+        P[i]["preset_mute_gain"] = 1.0
+    pcm = pcm_bytes(3, F, bit_depth, 501)
+    pcm[1] = pcm_q
+    sub_o = 4 if flavour == "q28" else 8
+    oracle.set_libm_f64(1)
+    eng = _engine(flavour, 3, F)
+    try:
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        spdif, pdm, status = eng.process_host(pcm, bit_depth, n_packets, fpp)
+        for i in range(3):
+            ch = _orc(oracle, flavour, P[i], bq[i])
+            ws, wp = _orc_run(oracle, flavour, ch, pcm[i], bit_depth, n_packets, fpp)
+            assert np.array_equal(spdif[i], ws), f"{case}: instance {i} S/PDIF words"
+            if P[i]["matrix"]["outputs"][sub_o]["enabled"]:
+                assert np.array_equal(pdm[i], wp), f"{case}: instance {i} PDM bits"
+            assert int(status[i]["clip_flags"]) == int(ch.clip_flags), f"{case}: instance {i} clip flags"
+            assert list(status[i]["peaks"]) == list(ch.peaks)[:len(status[i]["peaks"])]
+            if i == 1 and case == "clipping_hot_input":
+                assert int(status[i]["clip_flags"]) != 0
+            if i == 1 and case == "pdm_saturation" and flavour != "q28":
+                # the float path really drives (int32)(x * 2^28) out of range: some sub samples sit at the rails
+                assert int(ch.clip_flags) & (1 << 10)
+    finally:
+        eng.close()
+        oracle.set_libm_f64(0)
+
+
+# ---- preset-mute envelope inside and across calls ------------------------------------------------------------------------
+@pytest.mark.parametrize("flavour", ["f32f", "q28"])
+def test_preset_mute_envelope_runs_packet_by_packet(oracle, flavour):
+    """update_preset_mute_envelope() (usb_audio.c:466-498): a mute armed on some instances fades out, holds and fades
+    back in over the packets of two multi-packet calls; the others keep their constant gain."""
+    N, n_packets, fpp, calls = 12, 10, 96, 3
+    F = n_packets * fpp
+    P, bq = _params(oracle, flavour, N, 600)
+    armed = [i for i in range(N) if i % 3 != 2]
+    for i in range(N):
+        P[i]["host_mute"] = 0
+    pcm = pcm_bytes(N, F * calls, 24, 601)
+    sub_o = 4 if flavour == "q28" else 8
+    oracle.set_libm_f64(1)
+    eng = _engine(flavour, N, F)
+    try:
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        st = np.zeros(len(armed), L.PRESET_MUTE)
+        st["smooth_gain"] = 1.0
+        for k in range(len(armed)):
+            api.lib().dspi_preset_mute_arm(st[k:k + 1].ctypes.data_as(C.c_void_p), int(FS))
+        assert int(st["counter"][0]) == 960 and int(st["loading"][0]) == 1
+        chains = [_orc(oracle, flavour, P[i], bq[i]) for i in range(N)]
+        # armed instances need not be contiguous: one call per run
+        for k, i in enumerate(armed):
+            eng.set_preset_mute(st[k:k + 1], FS, inst0=i)
+            arm_mute_envelope(chains[i], FS)
+        for call in range(calls):
+            chunk = np.ascontiguousarray(pcm[:, call * F * 6:(call + 1) * F * 6])
+            spdif, pdm, _ = eng.process_host(chunk, 24, n_packets, fpp)
+            for i in range(N):
+                ws, wp = _orc_run(oracle, flavour, chains[i], chunk[i], 24, n_packets, fpp)
+                assert np.array_equal(spdif[i], ws), f"call {call} instance {i}: S/PDIF words"
+                if P[i]["matrix"]["outputs"][sub_o]["enabled"]:
+                    assert np.array_equal(pdm[i], wp), f"call {call} instance {i}: PDM bits"
+            got = eng.get_preset_mute()
+            for i in armed:
+                assert (int(got[i]["loading"]), int(got[i]["counter"])) == (int(chains[i].preset_loading), int(chains[i].preset_mute_counter))
+                assert np.float32(got[i]["smooth_gain"]) == np.float32(chains[i].preset_mute_smooth_gain)
+        assert all(float(got[i]["smooth_gain"]) == 1.0 and int(got[i]["loading"]) == 0 for i in armed)   # fade completed
+        # leaving envelope mode: the constant gain of set_params is back
+        eng.set_preset_mute(None, FS)
+        for i in armed:
+            chains[i].mute_env_on = 0
+            chains[i].preset_mute_gain = float(P[i]["preset_mute_gain"])      # the oracle record holds the envelope's last value
+        chunk = np.ascontiguousarray(pcm[:, :F * 6])
+        spdif, _, _ = eng.process_host(chunk, 24, n_packets, fpp)
+        for i in range(N):
+            ws, _ = _orc_run(oracle, flavour, chains[i], chunk[i], 24, n_packets, fpp)
+            assert np.array_equal(spdif[i], ws)
+    finally:
+        eng.close()
+        oracle.set_libm_f64(0)
+
+
+def test_host_envelope_step_matches_oracle(oracle):
+    for fs, fpp in [(96000, 96), (48000, 48), (44100, 45), (48000, 1), (96000, 192)]:
+        m = np.zeros(1, L.PRESET_MUTE)
+        m["smooth_gain"] = 1.0
+        api.lib().dspi_preset_mute_arm(m.ctypes.data_as(C.c_void_p), fs)
+        ld, cnt, g = C.c_uint8(1), C.c_uint32(int(m["counter"][0])), C.c_float(1.0)
+        for _ in range(200):
+            a = api.lib().dspi_preset_mute_step(m.ctypes.data_as(C.c_void_p), fpp, fs)
+            b = oracle.lib.orc_mute_envelope(C.byref(ld), C.byref(cnt), C.byref(g), fpp, fs)
+            assert np.float32(a) == np.float32(b) and int(m["counter"][0]) == cnt.value and int(m["loading"][0]) == ld.value
+
+
+# ---- round-1 advisor findings ---------------------------------------------------------------------------------------------
+def test_set_eq_params_device_right_after_an_asynchronous_process_call(oracle):
+    """process_device followed by set_eq_params_device without a sync: the running call must finish on the old
+    coefficients, the next call runs on the new ones (the edit used to race with the kernels in flight)."""
+    from dspi_b200 import workloads as W
+    N, n_packets, fpp = 16, 16, 96
+    F = n_packets * fpp
+    P, bq = chain_params(oracle, N, FS, 700, leveller=False)
+    pcm = pcm_bytes(N, F, 24, 701)
+    rec = np.stack([W.eq_params("B", L.CHAIN_EQ_CHANNELS, fs=FS, seed=900 + i) for i in range(N)])
+    oracle.set_libm_f64(1)
+    eng = api.ChainEngine("f32f", N, max_frames=F)
+    try:
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        d_pcm = torch.from_numpy(pcm).cuda()
+        d_sp = torch.zeros((N, 4, F, 2), dtype=torch.int32, device="cuda")
+        d_sp2 = torch.zeros_like(d_sp)
+        torch.cuda.synchronize()
+        eng.process_device(d_pcm.data_ptr(), 24, n_packets, fpp, spdif_ptr=d_sp.data_ptr())
+        eng.set_eq_params_device(rec, FS)                         # no sync in between
+        eng.process_device(d_pcm.data_ptr(), 24, n_packets, fpp, spdif_ptr=d_sp2.data_ptr())
+        eng.sync()
+        got1, got2 = d_sp.cpu().numpy(), d_sp2.cpu().numpy()
+        for i in range(N):
+            ch = make_orc_chain(oracle, P[i], bq[i])
+            ws, _ = orc_chain_run(oracle, "f32f", ch, pcm[i], 24, n_packets, fpp)
+            assert np.array_equal(got1[i], ws), f"instance {i}: first call disturbed by the coefficient edit"
+            filt = np.frombuffer(bytes(ch.filters), L.BIQUAD_F32).reshape(11, 12).copy()
+            r = rec[i].copy()
+            oracle.eq_coeffs(False, r, filt, FS)                  # dsp_compute_coefficients on the running state
+            C.memmove(C.addressof(ch.filters), filt.ctypes.data, 11 * 12 * 68)
+            for role in range(11):
+                ch.channel_bypassed[role] = 1 if all(int(filt[role, b]["bypass"]) for b in range(10)) else 0
+            ws2, _ = orc_chain_run(oracle, "f32f", ch, pcm[i], 24, n_packets, fpp)
+            assert np.array_equal(got2[i], ws2), f"instance {i}: second call"
+    finally:
+        eng.close()
+        oracle.set_libm_f64(0)
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "q28"])
+def test_state_import_restores_the_coefficient_mirror(oracle, flavour):
+    """Resume into a FRESH engine that never saw upload_biquads: download_biquads must return the checkpointed
+    coefficients and a later device-side edit must start from them (topology, bypass flags, state)."""
+    N, n_packets, fpp = 8, 4, 96
+    F = n_packets * fpp
+    P, bq = _params(oracle, flavour, N, 800, leveller=False)
+    pcm = pcm_bytes(N, 2 * F, 16, 801)
+    a = _engine(flavour, N, F)
+    b = _engine(flavour, N, F)
+    try:
+        a.set_params(P)
+        a.upload_biquads(bq)
+        a.process_host(np.ascontiguousarray(pcm[:, :F * 4]), 16, n_packets, fpp)
+        blob = a.state_export()
+        b.set_params(P)
+        b.state_import(blob)                                      # no upload_biquads on b
+        da, db = a.download_biquads(), b.download_biquads()
+        assert da.tobytes() == db.tobytes()
+        assert any(float(x) != 0.0 for x in np.asarray(db["b0"]).reshape(-1)[:50])
+        sa = a.process_host(np.ascontiguousarray(pcm[:, F * 4:]), 16, n_packets, fpp)
+        sb = b.process_host(np.ascontiguousarray(pcm[:, F * 4:]), 16, n_packets, fpp)
+        assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
+    finally:
+        a.close()
+        b.close()
+
+
+def test_pdm_rows_of_sub_disabled_instances_are_zero(oracle):
+    N, n_packets, fpp = 8, 3, 96
+    P, bq = chain_params(oracle, N, FS, 810, leveller=False)
+    for i in range(N):
+        P[i]["matrix"]["outputs"][8]["enabled"] = i % 2
+    pcm = pcm_bytes(N, n_packets * fpp, 16, 811)
+    eng = api.ChainEngine("f32f", N, max_frames=n_packets * fpp)
+    try:
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        for _ in range(2):
+            _, pdm, _ = eng.process_host(pcm, 16, n_packets, fpp)
+            assert not pdm[0::2].any() and pdm[1::2].any()
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "q28"])
+def test_volume_only_update_keeps_the_crossfeed_state(oracle, flavour):
+    """audio_set_volume() never touches crossfeed_state; only crossfeed_compute_coefficients() clears it."""
+    N, n_packets, fpp = 6, 4, 96
+    F = n_packets * fpp
+    P, bq = _params(oracle, flavour, N, 820, leveller=False)
+    for i in range(N):
+        P[i]["crossfeed_enabled"] = 1
+        P[i]["host_mute"] = 0
+        P[i]["preset_mute_gain"] = 1.0
+    pcm = pcm_bytes(N, 2 * F, 24, 821)
+    oracle.set_libm_f64(1)
+    eng = _engine(flavour, N, F)
+    try:
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        chains = [_orc(oracle, flavour, P[i], bq[i]) for i in range(N)]
+        c0 = np.ascontiguousarray(pcm[:, :F * 6])
+        eng.process_host(c0, 24, n_packets, fpp)
+        for i in range(N):
+            _orc_run(oracle, flavour, chains[i], c0[i], 24, n_packets, fpp)
+        vm, row = api.host_volume(-12 * 256)
+        P2 = P.copy()
+        for i in range(N):
+            P2[i]["host_vol_mul"] = vm                             # the record still carries the ZERO crossfeed state
+            chains[i].host_vol_mul = vm
+        eng.set_params(P2)
+        c1 = np.ascontiguousarray(pcm[:, F * 6:])
+        spdif, _, _ = eng.process_host(c1, 24, n_packets, fpp)
+        for i in range(N):
+            ws, _ = _orc_run(oracle, flavour, chains[i], c1[i], 24, n_packets, fpp)
+            assert np.array_equal(spdif[i], ws), f"instance {i}: crossfeed state was reset by a volume update"
+    finally:
+        eng.close()
+        oracle.set_libm_f64(0)
+
+
+# ---- BASELINE config 3 at its full instance count ------------------------------------------------------------------------
+@pytest.mark.parametrize("flavour", ["f32f", "q28"])
+def test_config3_full_instance_count_against_the_oracle(oracle, flavour):
+    """8192 device instances (65 536 S/PDIF channels + 8192 subs for the RP2350 shape), two 96-frame packets of packed
+    24-bit PCM: every 16th instance (and the first 64) against the oracle - words, PDM bits, meters."""
+    N, n_packets, fpp, tile = 8192, 2, 96, 64
+    F = n_packets * fpp
+    Pt, bqt = _params(oracle, flavour, tile, 900)
+    for i in range(tile):
+        Pt[i]["preset_mute_gain"] = 1.0
+    P = np.tile(Pt, N // tile)
+    bq = np.tile(bqt, (N // tile, 1, 1))
+    pcm = pcm_bytes(N, F, 24, 901)
+    sub_o = 4 if flavour == "q28" else 8
+    oracle.set_libm_f64(1)
+    eng = _engine(flavour, N, F)
+    try:
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        spdif, pdm, status = eng.process_host(pcm, 24, n_packets, fpp)
+        for i in list(range(64)) + list(range(64, N, 16)) + [N - 1]:
+            ch = _orc(oracle, flavour, P[i], bq[i])
+            ws, wp = _orc_run(oracle, flavour, ch, pcm[i], 24, n_packets, fpp)
+            assert np.array_equal(spdif[i], ws), f"instance {i}: S/PDIF words"
+            if P[i]["matrix"]["outputs"][sub_o]["enabled"]:
+                assert np.array_equal(pdm[i], wp), f"instance {i}: PDM bits"
+            assert int(status[i]["clip_flags"]) == int(ch.clip_flags)
+            assert list(status[i]["peaks"]) == list(ch.peaks)[:len(status[i]["peaks"])]
+    finally:
+        eng.close()
+        oracle.set_libm_f64(0)

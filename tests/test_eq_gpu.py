@@ -184,6 +184,23 @@ def test_full_size_properties(flavour, Cn):
     assert np.array_equal(y[1::512].view(np.uint32), x.view(np.uint32))
 
 
+@pytest.mark.parametrize("flavour,Cn,variant", [("f32f", 65536, "A"), ("f32f", 65536, "B"), ("f32s", 65536, "A"), ("q28", 32768, "B")])
+def test_full_size_every_channel_against_the_oracle(oracle, flavour, Cn, variant):
+    """BASELINE configs 2 / 4 at their full channel counts: every word of every channel against the CPU oracle
+    (two 96-frame packets; the oracle runs multithreaded), filter state included."""
+    import os
+    fs, T = 96000.0, 192
+    q = flavour == "q28"
+    params = W.eq_params_fast(variant, Cn, fs=fs, seed=5)
+    bq = api.compute_coefficients(params, q28=q, fs=fs)
+    x = W.inputs_q28(Cn, T) if q else W.inputs_f32(Cn, T)
+    y, st = _run_gpu(flavour, bq, x)
+    want, wst = x.copy(), bq.copy()
+    oracle.eq_many_mt(flavour, wst, want, 10, 96, min(32, os.cpu_count() or 1))
+    assert np.array_equal(y.view(np.uint32), want.view(np.uint32))
+    assert same_bits(st, wst)
+
+
 # ---- run-time specialised K1 (eq_jit.cu): same bits as the generic kernels and the oracle ----------
 def _run_gpu_info(flavour, bq, x, n_bands=10):
     Cn, T = x.shape
