@@ -183,7 +183,7 @@ def extra_configs(api, W, L, torch):
         p = W.eq_params_fast("B", 32768, fs=FS, seed=1)
         out["cfg4_q28_32768ch"] = _time_eq(api, torch, "q28", api.compute_coefficients(p, q28=True, fs=FS), 32768, T, q=True)
         # config 3: 8192 instances (65536 S/PDIF channels + 8192 PDM subs), s24 packets of 96 frames
-        N, fpp, npk = 8192, 96, 16
+        N, fpp, npk = 8192, 96, 64
         F = fpp * npk
         P, bq = W.chain_config3(N, fs=FS, seed=1)
         eng = api.ChainEngine("f32f", N, max_frames=F)
@@ -204,8 +204,9 @@ def extra_configs(api, W, L, torch):
         e1.record(st)
         eng.sync()
         ms = e0.elapsed_time(e1) / reps
+        part = eng.sm_partition()
         eng.close()
-        out["cfg3_full_chain_8192inst"] = {"instance_frames_per_s": N * F / (ms * 1e-3), "output_channel_samples_per_s": N * 9 * F / (ms * 1e-3),
+        out["cfg3_full_chain_8192inst"] = {"sm_partition": {"modulator": part[0], "other_stages": part[1]}, "instance_frames_per_s": N * F / (ms * 1e-3), "output_channel_samples_per_s": N * 9 * F / (ms * 1e-3),
                                            "ms_per_step": ms, "instances": N, "frames": F, "realtime_factor": (F / FS) / (ms * 1e-3),
                                            "bytes_per_instance_frame": {"pcm_in": 6, "spdif_out": 32, "pdm_out": 32}}
         # RP2040-shape Q28 chain: 8192 instances x (4 S/PDIF channels + 1 PDM sub)
@@ -215,16 +216,20 @@ def extra_configs(api, W, L, torch):
         engq.upload_biquads(bqq_all)
         spq = torch.empty((N, 2, F, 2), dtype=torch.int32, device="cuda")
         torch.cuda.synchronize()
+        stq = torch.cuda.ExternalStream(engq.stream)
         engq.process_device(pcm.data_ptr(), 24, npk, fpp, spq.data_ptr(), pdm.data_ptr())
         engq.sync()
-        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stq)
         for _ in range(reps):
             engq.process_device(pcm.data_ptr(), 24, npk, fpp, spq.data_ptr(), pdm.data_ptr())
+        e1.record(stq)
         engq.sync()
-        msq = (time.perf_counter() - t0) * 1e3 / reps
+        msq = e0.elapsed_time(e1) / reps
+        partq = engq.sm_partition()
         engq.close()
         out["cfg3_q28_chain_8192inst"] = {"instance_frames_per_s": N * F / (msq * 1e-3), "output_channel_samples_per_s": N * 5 * F / (msq * 1e-3),
-                                          "ms_per_step": msq, "instances": N, "frames": F, "realtime_factor": (F / FS) / (msq * 1e-3), "timing": "host clock around synchronised calls"}
+                                          "ms_per_step": msq, "instances": N, "frames": F, "realtime_factor": (F / FS) / (msq * 1e-3), "sm_partition": {"modulator": partq[0], "other_stages": partq[1]}}
         # S/PDIF subframe encoder (the step after the chain): 32768 stereo streams x 6144 frames, 24 B per frame
         ns, Fs = 4 * N, 6144
         nrot = 3                                                            # rotate buffers: 1.6 GB + 3.2 GB each, larger than L2
@@ -311,15 +316,9 @@ def main():
     kernel_info = eng.kernel_info()       # float engines compile K1 for their topology vector here, outside the timed region
 
     # rotating input buffers, each larger than L2 (126 MB): 65536 x 6144 x 4 B = 1.5 GiB
-    nbuf = max(2, min(8, args.steps))
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    bufs = []
-    for _ in range(nbuf):
-        if q:
-            b = torch.randint(-2**27, 2**27, (Cn, T), dtype=torch.int32, device="cuda", generator=gen)
-        else:
-            b = torch.rand((Cn, T), dtype=torch.float32, device="cuda", generator=gen) - 0.5
-        bufs.append(b)
+    # inputs: the per-channel xorshift32 streams of SURVEY 8(d) (seed 123456789 ^ absolute channel), generated on the GPU
+    nbuf = max(2, min(4, args.steps))
+    bufs = W.inputs_device(Cn, T, nbuf, q, torch.device("cuda", local_rank), ch0=ch0)
     torch.cuda.synchronize()
     stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
 
@@ -372,6 +371,7 @@ def main():
     # end to end through the C ABI with HOST buffers (pinned): H2D + kernel(s) + D2H inside the timed region
     e2e = None
     if not args.no_e2e:
+        numa_node = api.bind_host_to_device(local_rank)   # staging memory local to this GPU's PCIe root (before it is allocated)
         pin = api.PinnedBuffer((Cn, T), np.int32 if q else np.float32)
         src = bufs[0].cpu().numpy()
         pin.array[...] = src
@@ -388,7 +388,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": float(Cn) * T * n_e2e * world / dt, "unit": "samples/s", "h2d_bytes_per_step": Cn * T * 4 * world,
-               "d2h_bytes_per_step": Cn * T * 4 * world, "steps": n_e2e,
+               "d2h_bytes_per_step": Cn * T * 4 * world, "steps": n_e2e, "numa_node": numa_node,
                "path": "dspi_eq_process_host: pinned host [C][T] -> channel-chunked cudaMemcpyAsync H2D / kernel / D2H on 3 streams"}
         pin.free()
 
@@ -406,12 +406,15 @@ def main():
             full = torch.rand((total, T), dtype=torch.float32, device="cuda") - 0.5 if not q else \
                 torch.randint(-2**27, 2**27, (total, T), dtype=torch.int32, device="cuda")
         dt_t = torch.int32 if q else torch.float32
+        comp = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+
+        def process_range(shard, a, b):            # rows [a, b) of this rank's shard, in place, asynchronous on the engine stream
+            eng.process_device_range(shard[a:b].data_ptr(), T, T, a, b - a)
+
         def sg_step():
-            mine = sharding.scatter_rows(full, total, T, dt_t, "cuda")
+            sharding.pipelined_scatter_process_gather(full, total, T, dt_t, torch.device("cuda", local_rank), process_range, n_chunks=8,
+                                                      compute_stream=comp)
             torch.cuda.current_stream().synchronize()
-            eng.process_device(mine.data_ptr(), T, T)
-            eng.sync()
-            return sharding.gather_rows(mine, total)
         sg_step()
         dist.barrier()
         torch.cuda.synchronize()
@@ -423,7 +426,7 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         nccl = {"value": float(total) * T * n_sg / float(dt.item()), "unit": "samples/s", "steps": n_sg,
-                "path": "rank 0 holds all frames: grouped NCCL send/recv scatter -> per-rank kernel -> grouped gather to rank 0",
+                "path": "rank 0 holds all frames: 8 row chunks per shard, one grouped NCCL send/recv launch per step carries chunk j out and chunk j-2 back while the kernels work on chunk j-1 (sharding.pipelined_scatter_process_gather)",
                 "bytes_over_nvlink_per_step": int(total - Cn) * T * 4 * 2}
         del full
 
@@ -437,7 +440,7 @@ def main():
                 "dtype": {"f32f": "f32", "f32s": "f32", "q28": "int32"}[args.arith], "data": "synthetic",
                 "config": {"workload": workload, "channels_per_gpu": Cn, "frames_per_step": T, "sample_rate_hz": FS,
                            "arith": args.arith, "variant": args.variant, "parallelism": f"channel-sharded dp{world}, no collective on the data path",
-                           "l2": f"inputs larger than L2: {nbuf} rotating buffers of {Cn * T * 4 / 2**30:.2f} GiB", "layout": "channel-major [C][T], in place"},
+                           "l2": f"inputs larger than L2: {nbuf} rotating buffers of {Cn * T * 4 / 2**30:.2f} GiB", "inputs": "per-channel xorshift32 streams (seed 123456789 ^ channel), s16 / 65536", "layout": "channel-major [C][T], in place"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "nccl_scatter_gather": nccl, "other_configs": other,
                 "realtime_factor": value / (Cn * world * FS)}

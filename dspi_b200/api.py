@@ -35,6 +35,9 @@ SYMBOLS = [
     "dspi_bulk_state_defaults", "dspi_bulk_params_apply", "dspi_bulk_params_collect", "dspi_bulk_state_to_chain_f32", "dspi_bulk_state_to_chain_q28",
     "dspi_preset_slot_size", "dspi_crc32", "dspi_preset_slot_apply", "dspi_preset_slot_collect",
     "dspi_preamp", "dspi_master_volume", "dspi_preset_mute_arm", "dspi_preset_mute_step",
+    "dspi_chainq_stream", "dspi_eq_process_device_range", "dspi_bind_host_to_device", "dspi_eqx_create", "dspi_eqx_destroy", "dspi_eqx_shard_range",
+    "dspi_eqx_upload_biquads", "dspi_eqx_download_biquads", "dspi_eqx_process_host", "dspi_eqx_process_root", "dspi_eqx_launch_count",
+    "dspi_chain_set_dynamics_device", "dspi_chainq_set_dynamics_device", "dspi_chain_sm_partition", "dspi_chainq_sm_partition",
     "dspi_chain_set_preset_mute", "dspi_chain_get_preset_mute", "dspi_chainq_set_preset_mute", "dspi_chainq_get_preset_mute",
 ]
 
@@ -54,6 +57,11 @@ class _EqDesc(C.Structure):
 
 
 _lib = None
+
+
+class _EqxDesc(C.Structure):
+    _fields_ = [("arith", C.c_uint32), ("n_channels", C.c_uint32), ("n_bands", C.c_uint32), ("n_devices", C.c_uint32),
+                ("devices", C.c_int32 * 8), ("flags", C.c_uint32)]
 
 
 def lib():
@@ -106,6 +114,8 @@ def lib():
         h.dspi_chainq_process_host.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
         h.dspi_chainq_process_device.argtypes = [vp, vp, u32, u32, u32, vp, vp, vp]
         h.dspi_chainq_sync.argtypes = [vp]
+        h.dspi_chainq_stream.argtypes = [vp]
+        h.dspi_chainq_stream.restype = vp
         h.dspi_chainq_launch_count.argtypes = [vp]
         h.dspi_chainq_launch_count.restype = C.c_uint64
         h.dspi_crossfeed_compute_coefficients_q28.argtypes = [vp, vp, C.c_float]
@@ -123,6 +133,19 @@ def lib():
         for pre in ("dspi_chain", "dspi_chainq"):
             getattr(h, pre + "_set_preset_mute").argtypes = [vp, u32, u32, vp, u32]
             getattr(h, pre + "_get_preset_mute").argtypes = [vp, u32, u32, vp]
+            getattr(h, pre + "_set_dynamics_device").argtypes = [vp, u32, u32, vp, C.c_float]
+            getattr(h, pre + "_sm_partition").argtypes = [vp, vp, vp]
+        h.dspi_eq_process_device_range.argtypes = [vp, vp, u32, u32, u32, u32]
+        h.dspi_bind_host_to_device.argtypes = [C.c_int]
+        h.dspi_eqx_create.argtypes = [C.POINTER(vp), C.POINTER(_EqxDesc)]
+        h.dspi_eqx_destroy.argtypes = [vp]
+        h.dspi_eqx_shard_range.argtypes = [u32, u32, u32, vp, vp]
+        h.dspi_eqx_upload_biquads.argtypes = [vp, u32, u32, vp]
+        h.dspi_eqx_download_biquads.argtypes = [vp, u32, u32, vp]
+        h.dspi_eqx_process_host.argtypes = [vp, vp, u32]
+        h.dspi_eqx_process_root.argtypes = [vp, vp, u32, u32]
+        h.dspi_eqx_launch_count.argtypes = [vp]
+        h.dspi_eqx_launch_count.restype = C.c_uint64
         h.dspi_host_alloc.argtypes = [C.c_size_t]
         h.dspi_host_alloc.restype = vp
         h.dspi_host_free.argtypes = [vp]
@@ -216,6 +239,10 @@ class EqEngine:
     def process_device(self, dev_ptr, T, ld=None):
         _check(lib().dspi_eq_process_device(self._h, C.c_void_p(int(dev_ptr)), T, T if ld is None else ld))
 
+    def process_device_range(self, dev_ptr, T, ld, ch0, n):
+        """Channels [ch0, ch0+n) only; ``dev_ptr`` is the row of channel ch0."""
+        _check(lib().dspi_eq_process_device_range(self._h, C.c_void_p(int(dev_ptr)), int(T), int(ld), int(ch0), int(n)))
+
     def process_host(self, samples):
         """``samples``: C-contiguous [n_channels, T] numpy array (or PinnedBuffer.array); in place."""
         assert samples.flags["C_CONTIGUOUS"] and samples.dtype == self.sample_dtype and samples.shape[0] == self.n_channels
@@ -244,6 +271,60 @@ class EqEngine:
         buf = C.create_string_buffer(320)
         _check(lib().dspi_eq_kernel_info(self._h, buf, len(buf)))
         return buf.value.decode()
+
+
+class EqGroup:
+    """The EQ engine over several GPUs of one box, one process (``dspi_eqx_*``): contiguous channel shards, no exchange."""
+
+    def __init__(self, arith, n_channels, devices, n_bands=L.NUM_BANDS):
+        self.arith = ARITH[arith] if isinstance(arith, str) else int(arith)
+        self.q28 = self.arith == ARITH["q28"]
+        self.n_channels, self.devices = int(n_channels), list(devices)
+        d = _EqxDesc(self.arith, self.n_channels, int(n_bands), len(self.devices), (C.c_int32 * 8)(*(self.devices + [0] * (8 - len(self.devices)))), 0)
+        self._h = C.c_void_p()
+        _check(lib().dspi_eqx_create(C.byref(self._h), C.byref(d)))
+
+    def close(self):
+        if self._h:
+            lib().dspi_eqx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard_range(self, k):
+        lo, hi = C.c_uint32(), C.c_uint32()
+        _check(lib().dspi_eqx_shard_range(self.n_channels, len(self.devices), k, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def upload(self, biquads, ch0=0):
+        b = np.ascontiguousarray(biquads)
+        _check(lib().dspi_eqx_upload_biquads(self._h, int(ch0), int(b.shape[0]), b.ctypes.data))
+
+    def download(self, n=None, ch0=0):
+        n = self.n_channels - ch0 if n is None else n
+        out = np.zeros((n, L.MAX_BANDS), L.BIQUAD_Q28 if self.q28 else L.BIQUAD_F32)
+        _check(lib().dspi_eqx_download_biquads(self._h, int(ch0), int(n), out.ctypes.data))
+        return out
+
+    def process_host(self, samples):
+        assert samples.flags["C_CONTIGUOUS"] and samples.shape[0] == self.n_channels and samples.dtype.itemsize == 4
+        _check(lib().dspi_eqx_process_host(self._h, samples.ctypes.data, int(samples.shape[1])))
+
+    def process_root(self, dev_ptr, T, ld=None):
+        _check(lib().dspi_eqx_process_root(self._h, C.c_void_p(int(dev_ptr)), int(T), int(T if ld is None else ld)))
+
+    @property
+    def launch_count(self):
+        return int(lib().dspi_eqx_launch_count(self._h))
+
+
+def bind_host_to_device(device):
+    """NUMA-bind this thread and its future allocations to the device's PCIe node; returns the node or -1."""
+    return int(lib().dspi_bind_host_to_device(int(device)))
 
 
 class ChainEngine:
@@ -303,6 +384,17 @@ class ChainEngine:
     def state_import(self, blob):
         b = np.ascontiguousarray(blob, np.uint8)
         _check(getattr(lib(), "dspi_chain_state_import")(self._h, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size)))
+
+    def sm_partition(self):
+        """(SMs reserved for the modulator, SMs for every other stage); (0, 0) without a partition."""
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(getattr(lib(), self._PRE + "_sm_partition")(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_dynamics_device(self, cfgs, fs, inst0=0):
+        """DYNAMICS_CONFIG [n]: crossfeed / leveller / loudness coefficients and the host volume generated on the GPU."""
+        cf = np.ascontiguousarray(cfgs, L.DYNAMICS_CONFIG)
+        _check(getattr(lib(), self._PRE + "_set_dynamics_device")(self._h, int(inst0), int(cf.shape[0]), cf.ctypes.data_as(C.c_void_p), C.c_float(fs)))
 
     def set_preset_mute(self, states, fs, inst0=0, n=None):
         """Envelope mode for instances [inst0, inst0+n): ``states`` PRESET_MUTE [n], or None to leave envelope mode."""
@@ -553,6 +645,17 @@ class ChainEngineQ28:
         b = np.ascontiguousarray(blob, np.uint8)
         _check(getattr(lib(), "dspi_chainq_state_import")(self._h, b.ctypes.data_as(C.c_void_p), C.c_size_t(b.size)))
 
+    def sm_partition(self):
+        """(SMs reserved for the modulator, SMs for every other stage); (0, 0) without a partition."""
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(getattr(lib(), self._PRE + "_sm_partition")(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_dynamics_device(self, cfgs, fs, inst0=0):
+        """DYNAMICS_CONFIG [n]: crossfeed / leveller / loudness coefficients and the host volume generated on the GPU."""
+        cf = np.ascontiguousarray(cfgs, L.DYNAMICS_CONFIG)
+        _check(getattr(lib(), self._PRE + "_set_dynamics_device")(self._h, int(inst0), int(cf.shape[0]), cf.ctypes.data_as(C.c_void_p), C.c_float(fs)))
+
     def set_preset_mute(self, states, fs, inst0=0, n=None):
         """Envelope mode for instances [inst0, inst0+n): ``states`` PRESET_MUTE [n], or None to leave envelope mode."""
         if states is None:
@@ -590,6 +693,10 @@ class ChainEngineQ28:
 
     def sync(self):
         _check(lib().dspi_chainq_sync(self._h))
+
+    @property
+    def stream(self):
+        return lib().dspi_chainq_stream(self._h)
 
     @property
     def launch_count(self):

@@ -39,6 +39,7 @@
 #include "eq_kernels.cuh"
 #include "chain_pdm.cuh"
 #include "chain_streams.cuh"
+#include "dynamics.cuh"
 
 namespace dspi {
 namespace {
@@ -71,6 +72,7 @@ struct ChainDev {
     // preset-mute envelope (usb_audio.c:456-498): per-instance state and the per-packet volume it produces
     uint32_t *env;                                // [5][N_pad] loading, counter, smooth gain (float bits), sample rate, envelope mode on
     float *vol_base, *vol_master, *o_glin;        // [N_pad] host volume (:569), [N_pad] master volume, [9][N_pad] outputs[o].gain_linear
+    float *pmg;                                   // [N_pad] the constant preset_mute_gain of dspi_chain_set_params
     float *vmm;                                   // [packets of the call][N_pad] vol_mul_master (:571) of envelope-mode instances
 };
 
@@ -464,6 +466,57 @@ __global__ void chain_env_kernel(ChainDev d, uint32_t n_packets, uint32_t fpp)
     d.env[2 * Np + inst] = __float_as_uint(g);
 }
 
+// Mass reconfiguration of the dynamics stages on the device (SURVEY f-1): what the main loop does for one instance when
+// crossfeed_update_pending / leveller_update_pending / loudness_recompute_pending are set (main.c:868-895) plus
+// audio_set_volume() (usb_audio.c:428-440), one instance per thread, written straight into the engine's arrays.
+__global__ void chain_dynamics_kernel(ChainDev d, uint32_t inst0, uint32_t n, const dspi_dynamics_config *__restrict__ cfgs, float fs)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t inst = inst0 + i, Np = d.N_pad;
+    const dspi_dynamics_config cfg = cfgs[i];
+    uint8_t flags = d.flags[inst] & (uint8_t)~(F_XFEED | F_LEV | F_LOOKAHEAD | F_LOUD);
+    // crossfeed_compute_coefficients(): coefficients and CLEARED filter state (crossfeed.c:110-126)
+    float a0, b1, ap;
+    dyn::crossfeed_coeffs(cfg.crossfeed, fs, a0, b1, ap);
+    d.xf[0 * Np + inst] = a0; d.xf[1 * Np + inst] = b1; d.xf[4 * Np + inst] = ap;
+    d.xf[2 * Np + inst] = 0.0f; d.xf[3 * Np + inst] = 0.0f; d.xf[5 * Np + inst] = 0.0f; d.xf[6 * Np + inst] = 0.0f;
+    if (cfg.crossfeed.enabled) flags |= F_XFEED;                             // crossfeed_bypassed = !enabled, main.c:882
+    // leveller_compute_coefficients(); leveller_bypassed = !enabled, main.c:886-894
+    float lv[9];
+    dyn::leveller_coeffs(cfg.leveller, fs, lv);
+#pragma unroll
+    for (int k = 0; k < 9; k++) d.lev_c[k * Np + inst] = lv[k];
+    if (cfg.leveller.enabled) flags |= F_LEV;
+    if (cfg.leveller.lookahead) flags |= F_LOOKAHEAD;
+    // audio_set_volume(): vol_mul and the loudness row of that volume step; loudness_recompute_table() for that row
+    uint32_t row;
+    const int16_t vol_mul = dyn::host_volume(cfg.volume_8_8, row);
+    float lo_db, hi_db;
+    dyn::loudness_row_gains((int)row, cfg.loudness_ref_spl, cfg.loudness_intensity_pct, lo_db, hi_db);
+    float c[6];
+    bool byp;
+    uint8_t lb = 0;
+    const float lfs = fs < 1.0f ? 48000.0f : fs;                             // loudness.c:171
+    dyn::shelf_svf(200.0f, 0.707f, lo_db, false, lfs, c, byp);
+    if (byp) lb |= 1;
+#pragma unroll
+    for (int k = 0; k < 6; k++) d.loud_c[(0 * 6 + k) * Np + inst] = c[k];
+    dyn::shelf_svf(6000.0f, 0.707f, hi_db, true, lfs, c, byp);
+    if (byp) lb |= 2;
+#pragma unroll
+    for (int k = 0; k < 6; k++) d.loud_c[(1 * 6 + k) * Np + inst] = c[k];
+    d.loud_byp[inst] = lb;
+    if (cfg.loudness_enabled) flags |= F_LOUD;
+    d.flags[inst] = flags;
+    // host volume -> output gains (usb_audio.c:569-571, 886-887)
+    const float vol_base = cfg.host_mute ? 0.0f : __fmul_rn((float)vol_mul, 1.0f / 32768.0f);
+    d.vol_base[inst] = vol_base;
+    const float vmm = __fmul_rn(__fmul_rn(vol_base, d.pmg[inst]), d.vol_master[inst]);
+    for (int o = 0; o < kOuts; o++)
+        d.o_gain[o * Np + inst] = (d.o_flags[o * Np + inst] & O_MUTE) ? 0.0f : __fmul_rn(d.o_glin[o * Np + inst], vmm);
+}
+
 // post-gain sample of output row `o` (what the delay line stores)
 __device__ __forceinline__ float out_gain(float v, bool enabled, float gain)
 {
@@ -747,7 +800,8 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
     // Stage pipeline over packet slices on three streams (chain_streams.cuh): front stages of slice
     // i+1 overlap the output stages of slice i and the modulator of slice i-1.
     dspi::ChainStreams &st = c->st;
-    const uint32_t n_slices = n_packets < (uint32_t)dspi::ChainStreams::kMaxSlices ? n_packets : (uint32_t)dspi::ChainStreams::kMaxSlices;
+    uint32_t slice_bounds[dspi::ChainStreams::kMaxSlices + 1];
+    const uint32_t n_slices = (uint32_t)dspi::ChainStreams::plan_slices(n_packets, slice_bounds);
     if (c->env_instances) {                                                  // preset-mute envelope: this call's per-packet volumes
         if (c->vmm_packets < n_packets) {
             CU_OK(cudaStreamSynchronize(c->stream));
@@ -761,11 +815,11 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
         c->launches++;
     }
     const ChainDev d = c->d;
-    const uint32_t n_sms = 148;
+    const uint32_t n_sms = st.rest_sms ? st.rest_sms : 148;     // SMs the streaming stages run on (chain_streams.cuh)
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
     CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
-        const uint32_t p0 = (uint32_t)((uint64_t)n_packets * sl / n_slices), p1 = (uint32_t)((uint64_t)n_packets * (sl + 1) / n_slices);
+        const uint32_t p0 = slice_bounds[sl], p1 = slice_bounds[sl + 1];
         const uint32_t fb = p0 * fpp, fe = p1 * fpp;
         int rc;
         // ---- front: unpack + loudness -> master EQ (K1) -> leveller + crossfeed
@@ -881,7 +935,7 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
         if (rc != DSPI_OK) { dspi_chain_destroy(c); return rc; }
     }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = c->st.create();
+    if (e == cudaSuccess) e = c->st.create(desc->device, desc->n_instances);
 #define TRY(x) if (e == cudaSuccess) e = (x)
     TRY(dev_alloc(c, &c->d_aos, Np * dspi::kRoles * DSPI_MAX_BANDS));
     TRY(dev_alloc(c, &d.preamp, 2 * Np));
@@ -915,6 +969,7 @@ int dspi_chain_create(dspi_chain **out, const dspi_chain_desc *desc)
     TRY(dev_alloc(c, &d.vol_base, Np));
     TRY(dev_alloc(c, &d.vol_master, Np));
     TRY(dev_alloc(c, &d.o_glin, dspi::kOuts * Np));
+    TRY(dev_alloc(c, &d.pmg, Np));
     TRY(init_states(c));
 #undef TRY
     if (e != cudaSuccess) {
@@ -942,7 +997,7 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
     CU_OK(cudaSetDevice(c->desc.device));
     const ChainDev &d = c->d;
     const size_t Np = d.N_pad;
-    std::vector<float> preamp(2 * n), loud_c(12 * n), xf(7 * n), lev_c(9 * n), gl(9 * n), gr(9 * n), gain(9 * n), glin(9 * n), vbase(n), vmaster(n);
+    std::vector<float> preamp(2 * n), loud_c(12 * n), xf(7 * n), lev_c(9 * n), gl(9 * n), gr(9 * n), gain(9 * n), glin(9 * n), vbase(n), vmaster(n), pmgv(n);
     std::vector<uint8_t> flags(n), loud_byp(n), oflags(9 * n), skip_m(2 * n), skip_o(9 * n);
     std::vector<int32_t> dly(9 * n);
     std::vector<float> xf_cur(7 * n);
@@ -954,6 +1009,7 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
         float vol_mul = p.host_mute ? 0.0f : (float)p.host_vol_mul * (1.0f / 32768.0f);
         vbase[i] = vol_mul;
         vmaster[i] = p.master_volume_linear;
+        pmgv[i] = p.preset_mute_gain;
         vol_mul *= p.preset_mute_gain;
         const float vol_mul_master = vol_mul * p.master_volume_linear;
         preamp[0 * n + i] = p.preamp_linear[0];
@@ -1021,6 +1077,7 @@ int dspi_chain_set_params(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_
     CU_OK(put(d.o_glin, glin.data(), 9, 4));
     CU_OK(put(d.vol_base, vbase.data(), 1, 4));
     CU_OK(put(d.vol_master, vmaster.data(), 1, 4));
+    CU_OK(put(d.pmg, pmgv.data(), 1, 4));
     CU_OK(put(d.o_flags, oflags.data(), 9, 1));
     CU_OK(put(d.o_dly, dly.data(), 9, 4));
     CU_OK(put(d.skip_m, skip_m.data(), 2, 1));
@@ -1075,6 +1132,27 @@ int dspi_chain_get_preset_mute(dspi_chain *c, uint32_t inst0, uint32_t n, dspi_p
         states[i].counter = rows[1 * n + i];
         memcpy(&states[i].smooth_gain, &rows[2 * n + i], 4);
     }
+    return DSPI_OK;
+}
+
+/* crossfeed / leveller / loudness coefficients and the host volume of instances [inst0, inst0+n) generated ON THE GPU */
+int dspi_chain_set_dynamics_device(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_dynamics_config *cfgs, float sample_rate)
+{
+    if (!c || !cfgs) return fail(DSPI_EINVAL, "null argument");
+    if ((uint64_t)inst0 + n > c->desc.n_instances) return fail(DSPI_ERANGE, "instances [%u, %u) outside engine of %u", inst0, inst0 + n, c->desc.n_instances);
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(c->desc.device));
+    dspi_dynamics_config *d_cfg = nullptr;
+    CU_OK(cudaMalloc((void **)&d_cfg, (size_t)n * sizeof(*cfgs)));
+    cudaError_t e = cudaMemcpyAsync(d_cfg, cfgs, (size_t)n * sizeof(*cfgs), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        dspi::chain_dynamics_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d, inst0, n, d_cfg, sample_rate);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_cfg);
+    if (e != cudaSuccess) return fail(DSPI_ECUDA, "dynamics coefficient generation: %s", cudaGetErrorString(e));
+    c->launches++;
     return DSPI_OK;
 }
 
@@ -1279,6 +1357,15 @@ int dspi_chain_sync(dspi_chain *c)
 }
 
 void *dspi_chain_stream(dspi_chain *c) { return c ? (void *)c->stream : nullptr; }
+/* SMs reserved for the modulator / left to every other stage (0, 0: no partition, see chain_streams.cuh) */
+int dspi_chain_sm_partition(dspi_chain *c, uint32_t *pdm_sms, uint32_t *rest_sms)
+{
+    if (!c) return fail(DSPI_EINVAL, "null argument");
+    if (pdm_sms) *pdm_sms = c->st.pdm_sms;
+    if (rest_sms) *rest_sms = c->st.rest_sms;
+    return DSPI_OK;
+}
+
 uint64_t dspi_chain_launch_count(dspi_chain *c)
 {
     return c ? c->launches + dspi_eq_launch_count(c->eq_m) + dspi_eq_launch_count(c->eq_o) : 0;

@@ -20,6 +20,7 @@
 #include "eq_kernels.cuh"
 #include "chain_pdm.cuh"
 #include "chain_streams.cuh"
+#include "dynamics.cuh"
 
 namespace dspi {
 namespace {
@@ -55,6 +56,7 @@ struct ChainQ {
     uint32_t *env;                                 // [5][N_pad] loading, counter, smooth gain (float bits), sample rate, envelope mode on
     int32_t *vol_base, *vol_master;                // [N_pad] host volume Q15 (:975), master_volume_q15
     float *o_glin;                                 // [5][N_pad] outputs[o].gain_linear
+    int32_t *pmg;                                  // [N_pad] the constant preset_mute_gain of dspi_chainq_set_params, as Q15 (:976-978)
     int32_t *vmm;                                  // [packets of the call][N_pad] vol_mul_master (:980) of envelope-mode instances
 };
 
@@ -432,6 +434,55 @@ __global__ void chainq_env_kernel(ChainQ d, uint32_t n_packets, uint32_t fpp)
     d.env[2 * Np + inst] = __float_as_uint(g);
 }
 
+// Mass reconfiguration of the dynamics stages on the device (SURVEY f-1), RP2040 stores: see chain_f32.cu
+__global__ void chainq_dynamics_kernel(ChainQ d, uint32_t inst0, uint32_t n, const dspi_dynamics_config *__restrict__ cfgs, float fs)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t inst = inst0 + i;
+    const size_t Np = d.N_pad;
+    const dspi_dynamics_config cfg = cfgs[i];
+    uint8_t flags = d.flags[inst] & (uint8_t)~(F_XFEED | F_LEV | F_LOOKAHEAD | F_LOUD);
+    float a0, b1, ap;
+    const bool xon = dyn::crossfeed_coeffs(cfg.crossfeed, fs, a0, b1, ap);
+    const float scale = 268435456.0f;                                        // crossfeed.c:115-118
+    d.xf[0 * Np + inst] = xon ? dyn::f2i_sat(__fmul_rn(a0, scale)) : 0;
+    d.xf[1 * Np + inst] = xon ? dyn::f2i_sat(__fmul_rn(b1, scale)) : 0;
+    d.xf[4 * Np + inst] = xon ? dyn::f2i_sat(__fmul_rn(ap, scale)) : 0;
+    d.xf[2 * Np + inst] = 0; d.xf[3 * Np + inst] = 0; d.xf[5 * Np + inst] = 0; d.xf[6 * Np + inst] = 0;
+    if (cfg.crossfeed.enabled) flags |= F_XFEED;
+    float lv[9];
+    dyn::leveller_coeffs(cfg.leveller, fs, lv);
+#pragma unroll
+    for (int k = 0; k < 9; k++) d.lev_c[k * Np + inst] = lv[k];
+    if (cfg.leveller.enabled) flags |= F_LEV;
+    if (cfg.leveller.lookahead) flags |= F_LOOKAHEAD;
+    uint32_t row;
+    const int16_t vol_mul = dyn::host_volume(cfg.volume_8_8, row);
+    float lo_db, hi_db;
+    dyn::loudness_row_gains((int)row, cfg.loudness_ref_spl, cfg.loudness_intensity_pct, lo_db, hi_db);
+    int32_t c[5];
+    bool byp;
+    uint8_t lb = 0;
+    const float lfs = fs < 1.0f ? 48000.0f : fs;
+    dyn::shelf_q28(200.0f, 0.707f, lo_db, false, lfs, c, byp);
+    if (byp) lb |= 1;
+#pragma unroll
+    for (int k = 0; k < 5; k++) d.loud_c[(0 * 5 + k) * Np + inst] = c[k];
+    dyn::shelf_q28(6000.0f, 0.707f, hi_db, true, lfs, c, byp);
+    if (byp) lb |= 2;
+#pragma unroll
+    for (int k = 0; k < 5; k++) d.loud_c[(1 * 5 + k) * Np + inst] = c[k];
+    d.loud_byp[inst] = lb;
+    if (cfg.loudness_enabled) flags |= F_LOUD;
+    d.flags[inst] = flags;
+    const int32_t vol_base = cfg.host_mute ? 0 : (int32_t)vol_mul;           // usb_audio.c:975
+    d.vol_base[inst] = vol_base;
+    const int32_t vmm = mul_q15(mul_q15(vol_base, d.pmg[inst]), d.vol_master[inst]);    // :979-980
+    for (int o = 0; o < kOuts; o++)
+        d.o_gain[o * Np + inst] = (d.o_flags[o * Np + inst] & O_MUTE) ? 0 : __float2int_rz(__fmul_rn(d.o_glin[o * Np + inst], (float)vmm));   // :1204-1205
+}
+
 __device__ __forceinline__ int32_t outq_gain(int32_t v, bool enabled, int32_t gain)
 {
     if (enabled) v = (gain == 0) ? 0 : mul_q15(v, gain);
@@ -760,7 +811,7 @@ int dspi_chainq_create(dspi_chainq **out, const dspi_chain_desc *desc)
         if (rc != DSPI_OK) { dspi_chainq_destroy(c); return rc; }
     }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = c->st.create();
+    if (e == cudaSuccess) e = c->st.create(desc->device, desc->n_instances);
 #define TRY(x) if (e == cudaSuccess) e = (x)
     TRY(dev_alloc(c, &c->d_aos, Np * dspi::kRoles * DSPI_MAX_BANDS));
     TRY(dev_alloc(c, &d.preamp, 2 * Np));
@@ -795,6 +846,7 @@ int dspi_chainq_create(dspi_chainq **out, const dspi_chain_desc *desc)
     TRY(dev_alloc(c, &d.vol_base, Np));
     TRY(dev_alloc(c, &d.vol_master, Np));
     TRY(dev_alloc(c, &d.o_glin, dspi::kOuts * Np));
+    TRY(dev_alloc(c, &d.pmg, Np));
     // every band of every channel starts bypassed (dsp_init_default_filters, dsp_pipeline.c:177-199)
     if (e == cudaSuccess) {
         std::vector<dspi_biquad_q28> byp(Np * dspi::kRoles * DSPI_MAX_BANDS);
@@ -838,7 +890,7 @@ int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dsp
     const int O = dspi::kOuts;
     std::vector<int32_t> preamp(2 * n), loud_c(10 * n), xf(7 * n), gl(O * n), gr(O * n), gain(O * n), dly(O * n);
     std::vector<float> lev_c(9 * n), glin(O * n);
-    std::vector<int32_t> vbase(n), vmaster(n);
+    std::vector<int32_t> vbase(n), vmaster(n), pmgv(n);
     std::vector<uint8_t> flags(n), loud_byp(n), oflags(O * n), skip_m(2 * n), skip_o(O * n);
     std::vector<int32_t> xf_cur(7 * n);
     CU_OK(cudaMemcpy2DAsync(xf_cur.data(), (size_t)n * 4, d.xf + inst0, Np * 4, (size_t)n * 4, 7, cudaMemcpyDeviceToHost, c->stream));
@@ -851,6 +903,7 @@ int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dsp
         int32_t pmg = (int32_t)(p.preset_mute_gain * 32768.0f + 0.5f);                                  // :976-978
         if (pmg < 0) pmg = 0;
         if (pmg > 32768) pmg = 32768;
+        pmgv[i] = pmg;
         vol_mul = dspi::h_mul_q15(vol_mul, pmg);                                                        // :979
         const int32_t vol_mul_master = dspi::h_mul_q15(vol_mul, p.master_volume_q15);                   // :980
         preamp[0 * n + i] = p.preamp_q28[0];
@@ -912,6 +965,7 @@ int dspi_chainq_set_params(dspi_chainq *c, uint32_t inst0, uint32_t n, const dsp
     CU_OK(put(d.o_glin, glin.data(), O, 4));
     CU_OK(put(d.vol_base, vbase.data(), 1, 4));
     CU_OK(put(d.vol_master, vmaster.data(), 1, 4));
+    CU_OK(put(d.pmg, pmgv.data(), 1, 4));
     CU_OK(put(d.o_flags, oflags.data(), O, 1));
     CU_OK(put(d.o_dly, dly.data(), O, 4));
     CU_OK(put(d.skip_m, skip_m.data(), 2, 1));
@@ -966,6 +1020,27 @@ int dspi_chainq_get_preset_mute(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi
         states[i].counter = rows[1 * n + i];
         memcpy(&states[i].smooth_gain, &rows[2 * n + i], 4);
     }
+    return DSPI_OK;
+}
+
+/* crossfeed / leveller / loudness coefficients and the host volume of instances [inst0, inst0+n) generated ON THE GPU */
+int dspi_chainq_set_dynamics_device(dspi_chainq *c, uint32_t inst0, uint32_t n, const dspi_dynamics_config *cfgs, float sample_rate)
+{
+    if (!c || !cfgs) return fail(DSPI_EINVAL, "null argument");
+    if ((uint64_t)inst0 + n > c->desc.n_instances) return fail(DSPI_ERANGE, "instances [%u, %u) outside engine of %u", inst0, inst0 + n, c->desc.n_instances);
+    if (n == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(c->desc.device));
+    dspi_dynamics_config *d_cfg = nullptr;
+    CU_OK(cudaMalloc((void **)&d_cfg, (size_t)n * sizeof(*cfgs)));
+    cudaError_t e = cudaMemcpyAsync(d_cfg, cfgs, (size_t)n * sizeof(*cfgs), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        dspi::chainq_dynamics_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->d, inst0, n, d_cfg, sample_rate);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_cfg);
+    if (e != cudaSuccess) return fail(DSPI_ECUDA, "dynamics coefficient generation: %s", cudaGetErrorString(e));
+    c->launches++;
     return DSPI_OK;
 }
 
@@ -1055,7 +1130,8 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
     }
     // Stage pipeline over packet slices on three streams (chain_streams.cuh), stages as in chain_f32.cu.
     dspi::ChainStreams &st = c->st;
-    const uint32_t n_slices = n_packets < (uint32_t)dspi::ChainStreams::kMaxSlices ? n_packets : (uint32_t)dspi::ChainStreams::kMaxSlices;
+    uint32_t slice_bounds[dspi::ChainStreams::kMaxSlices + 1];
+    const uint32_t n_slices = (uint32_t)dspi::ChainStreams::plan_slices(n_packets, slice_bounds);
     if (c->env_instances) {                                                  // preset-mute envelope: this call's per-packet volumes
         if (c->vmm_packets < n_packets) {
             CU_OK(cudaStreamSynchronize(c->stream));
@@ -1069,11 +1145,11 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
         c->launches++;
     }
     const ChainQ d = c->d;
-    const uint32_t n_sms = 148;
+    const uint32_t n_sms = st.rest_sms ? st.rest_sms : 148;     // SMs the streaming stages run on (chain_streams.cuh)
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
     CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
-        const uint32_t p0 = (uint32_t)((uint64_t)n_packets * sl / n_slices), p1 = (uint32_t)((uint64_t)n_packets * (sl + 1) / n_slices);
+        const uint32_t p0 = slice_bounds[sl], p1 = slice_bounds[sl + 1];
         const uint32_t fb = p0 * fpp, fe = p1 * fpp;
         int rc;
         dspi::chainq_pre_kernel<<<(d.N_pad / 32 + 1) / 2, 64, 0, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, fb, fe, F);
@@ -1224,6 +1300,16 @@ int dspi_chainq_sync(dspi_chainq *c)
     return DSPI_OK;
 }
 
+/* SMs reserved for the modulator / left to every other stage (0, 0: no partition, see chain_streams.cuh) */
+int dspi_chainq_sm_partition(dspi_chainq *c, uint32_t *pdm_sms, uint32_t *rest_sms)
+{
+    if (!c) return fail(DSPI_EINVAL, "null argument");
+    if (pdm_sms) *pdm_sms = c->st.pdm_sms;
+    if (rest_sms) *rest_sms = c->st.rest_sms;
+    return DSPI_OK;
+}
+
+void *dspi_chainq_stream(dspi_chainq *c) { return c ? (void *)c->stream : nullptr; }
 uint64_t dspi_chainq_launch_count(dspi_chainq *c)
 {
     return c ? c->launches + dspi_eq_launch_count(c->eq_m) + dspi_eq_launch_count(c->eq_o) : 0;

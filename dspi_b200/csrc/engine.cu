@@ -10,6 +10,9 @@
 #include <new>
 #include <utility>
 #include <vector>
+#include <sched.h>
+#include <unistd.h>
+#include <sys/syscall.h>
 
 #include "eq_kernels.cuh"
 #include "eq_jit.h"
@@ -114,6 +117,55 @@ void *dspi_host_alloc(size_t bytes)
     return p;
 }
 void dspi_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+/* Pin the calling thread (and the pages it touches from now on) to the NUMA node the GPU's PCIe link hangs off, so
+ * that pinned staging memory allocated afterwards is local to the link and host <-> device copies do not cross the
+ * socket interconnect.  Linux sysfs only; returns the node (>= 0), or -1 when the topology is unknown (nothing changed). */
+int dspi_bind_host_to_device(int device)
+{
+    char bus[32] = { 0 };
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *p = bus; *p; p++) if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return -1;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return -1;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int lo = 0, hi = 0, n = 0;
+    char sep = 0;
+    while (fscanf(f, "%d", &lo) == 1) {                                     /* "0-31,64-95" */
+        hi = lo;
+        if (fscanf(f, "%c", &sep) == 1 && sep == '-') { if (fscanf(f, "%d", &hi) != 1) hi = lo; if (fscanf(f, "%c", &sep) != 1) sep = 0; }
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); n++; }
+        if (sep != ',') break;
+    }
+    fclose(f);
+    if (n == 0) return -1;
+    cpu_set_t allowed;                                                       /* stay inside the cpuset this process was given */
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        cpu_set_t both;
+        CPU_AND(&both, &set, &allowed);
+        if (CPU_COUNT(&both) == 0) return -1;
+        set = both;
+    }
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return -1;
+#ifdef SYS_set_mempolicy
+    if (node < 1024) {                                                       /* MPOL_PREFERRED = 1: fall back to other nodes when full */
+        unsigned long mask[16] = { 0 };
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        syscall(SYS_set_mempolicy, 1, mask, (unsigned long)(sizeof(mask) * 8));
+    }
+#endif
+    return node;
+}
 
 int dspi_eq_create(dspi_eq **out, const dspi_eq_desc *desc)
 {
@@ -509,15 +561,29 @@ int dspi_eq_process_device(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld)
     return launch_eq(e, d_samples, T, ld, 0, e->n_groups, e->desc.n_channels, e->stream);
 }
 
-int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T)
+int dspi_eq_process_device_range(dspi_eq *e, void *d_rows, uint32_t T, uint32_t ld, uint32_t ch0, uint32_t n)
 {
-    if (!e || !h_samples) return fail(DSPI_EINVAL, "null argument");
-    if (T == 0) return DSPI_OK;
+    if (!e || !d_rows) return fail(DSPI_EINVAL, "null argument");
+    if (T == 0 || n == 0) return DSPI_OK;
+    if (ld < T) return fail(DSPI_EINVAL, "row stride %u < T %u", ld, T);
+    if ((uint64_t)ch0 + n > e->desc.n_channels) return fail(DSPI_ERANGE, "channels [%u, %u) outside engine of %u", ch0, ch0 + n, e->desc.n_channels);
+    if (ch0 % e->rows) return fail(DSPI_EINVAL, "first channel %u is not a multiple of the engine's group size %u", ch0, e->rows);
     CU_OK(cudaSetDevice(e->desc.device));
-    const uint32_t C = e->desc.n_channels;
-    // channel-chunked pipeline: rows [c0, c1) x T are contiguous in the caller's [C][T] array, so every
-    // copy is one large 1-D transfer at full PCIe rate; H2D, kernel and D2H of consecutive chunks
-    // overlap on three streams.  Channels are independent, so chunk order and size change no bit.
+    return launch_eq(e, d_rows, T, ld, ch0 / e->rows, (n + e->rows - 1) / e->rows, n, e->stream);
+}
+
+}  // extern "C"
+
+// The staged pipeline behind dspi_eq_process_host and the multi-device group (eqx.cu): rows [c0, c1) x T are contiguous in
+// the caller's [C][T] array, so every copy is one large 1-D transfer at full link rate; copy-in, kernel and copy-out of
+// consecutive chunks overlap on three streams, which also keeps BOTH directions of the link busy.  `remote` may be pinned
+// host memory (PCIe) or memory of a peer GPU with peer access enabled (NVLink): cudaMemcpyDefault resolves either.
+// Channels are independent, so chunk order and size change no bit.  enqueue returns without waiting.
+namespace dspi {
+int eq_process_remote_enqueue(dspi_eq *e, void *remote, uint32_t T, uint32_t ch0, uint32_t n_ch)
+{
+    if (T == 0 || n_ch == 0) return DSPI_OK;
+    CU_OK(cudaSetDevice(e->desc.device));
     const uint32_t ld = (T + 3) & ~3u;                                      // device rows padded for TMA
     uint32_t cc = (uint32_t)(((size_t)96 << 20) / ((size_t)ld * 4));
     cc = cc / e->rows * e->rows;
@@ -525,6 +591,7 @@ int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T)
     if (cc > e->c_pad) cc = e->c_pad;
     const size_t need = (size_t)cc * ld * 4;
     if (need > e->stage_bytes) {
+        CU_OK(cudaStreamSynchronize(e->s_d2h));
         for (int i = 0; i < kHostBufs; i++) {
             if (e->d_stage[i]) { cudaFree(e->d_stage[i]); e->d_stage[i] = nullptr; }
         }
@@ -534,27 +601,45 @@ int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T)
         }
         e->stage_bytes = need;
     }
-    const uint32_t nchunks = (C + cc - 1) / cc;
-    char *host = (char *)h_samples;
+    const uint32_t nchunks = (n_ch + cc - 1) / cc;
+    char *base = (char *)remote;
     for (uint32_t k = 0; k < nchunks; k++) {
         const int b = k % kHostBufs;
-        const uint32_t c0 = k * cc, n = (C - c0 < cc) ? (C - c0) : cc;
-        char *hp = host + (size_t)c0 * T * 4;
-        if (k >= (uint32_t)kHostBufs) CU_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_out[b], 0));       // buffer drained
-        if (ld == T) CU_OK(cudaMemcpyAsync(e->d_stage[b], hp, (size_t)n * T * 4, cudaMemcpyHostToDevice, e->s_h2d));
-        else CU_OK(cudaMemcpy2DAsync(e->d_stage[b], (size_t)ld * 4, hp, (size_t)T * 4, (size_t)T * 4, n, cudaMemcpyHostToDevice, e->s_h2d));
+        const uint32_t c0 = k * cc, n = (n_ch - c0 < cc) ? (n_ch - c0) : cc;
+        char *hp = base + (size_t)c0 * T * 4;
+        CU_OK(cudaStreamWaitEvent(e->s_h2d, e->ev_out[b], 0));                                      // buffer drained (also by an earlier call)
+        if (ld == T) CU_OK(cudaMemcpyAsync(e->d_stage[b], hp, (size_t)n * T * 4, cudaMemcpyDefault, e->s_h2d));
+        else CU_OK(cudaMemcpy2DAsync(e->d_stage[b], (size_t)ld * 4, hp, (size_t)T * 4, (size_t)T * 4, n, cudaMemcpyDefault, e->s_h2d));
         CU_OK(cudaEventRecord(e->ev_in[b], e->s_h2d));
         CU_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
-        int rc = launch_eq(e, e->d_stage[b], T, ld, c0 / e->rows, (n + e->rows - 1) / e->rows, n, e->stream);
+        int rc = launch_eq(e, e->d_stage[b], T, ld, (ch0 + c0) / e->rows, (n + e->rows - 1) / e->rows, n, e->stream);
         if (rc) return rc;
         CU_OK(cudaEventRecord(e->ev_done[b], e->stream));
         CU_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[b], 0));
-        if (ld == T) CU_OK(cudaMemcpyAsync(hp, e->d_stage[b], (size_t)n * T * 4, cudaMemcpyDeviceToHost, e->s_d2h));
-        else CU_OK(cudaMemcpy2DAsync(hp, (size_t)T * 4, e->d_stage[b], (size_t)ld * 4, (size_t)T * 4, n, cudaMemcpyDeviceToHost, e->s_d2h));
+        if (ld == T) CU_OK(cudaMemcpyAsync(hp, e->d_stage[b], (size_t)n * T * 4, cudaMemcpyDefault, e->s_d2h));
+        else CU_OK(cudaMemcpy2DAsync(hp, (size_t)T * 4, e->d_stage[b], (size_t)ld * 4, (size_t)T * 4, n, cudaMemcpyDefault, e->s_d2h));
         CU_OK(cudaEventRecord(e->ev_out[b], e->s_d2h));
     }
+    return DSPI_OK;
+}
+
+int eq_process_remote_wait(dspi_eq *e)
+{
+    CU_OK(cudaSetDevice(e->desc.device));
     CU_OK(cudaStreamSynchronize(e->s_d2h));
     return DSPI_OK;
+}
+}  // namespace dspi
+
+extern "C" {
+
+int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T)
+{
+    if (!e || !h_samples) return fail(DSPI_EINVAL, "null argument");
+    if (T == 0) return DSPI_OK;
+    int rc = dspi::eq_process_remote_enqueue(e, h_samples, T, 0, e->desc.n_channels);
+    if (rc) return rc;
+    return dspi::eq_process_remote_wait(e);
 }
 
 int dspi_eq_sync(dspi_eq *e)

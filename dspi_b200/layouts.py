@@ -159,3 +159,11 @@ BULK_STATE = np.dtype({
 # dspi_preset_mute (include/dspi_b200.h): state of update_preset_mute_envelope(), usb_audio.c:456-498
 PRESET_MUTE = np.dtype([("loading", "u1"), ("reserved", "u1", (3,)), ("counter", "<u4"), ("smooth_gain", "<f4")])
 assert PRESET_MUTE.itemsize == 12
+
+# dspi_dynamics_config (include/dspi_b200.h): crossfeed_config + leveller_config + loudness globals + host volume
+DYNAMICS_CONFIG = np.dtype([
+    ("xf_enabled", "u1"), ("xf_itd_enabled", "u1"), ("xf_preset", "u1"), ("_p0", "u1"), ("xf_custom_fc", "<f4"), ("xf_custom_feed_db", "<f4"),
+    ("lev_enabled", "u1"), ("_p1", "u1", (3,)), ("lev_amount", "<f4"), ("lev_speed", "u1"), ("_p2", "u1", (3,)), ("lev_max_gain_db", "<f4"),
+    ("lev_lookahead", "u1"), ("_p3", "u1", (3,)), ("lev_gate_threshold_db", "<f4"),
+    ("loudness_ref_spl", "<f4"), ("loudness_intensity_pct", "<f4"), ("loudness_enabled", "u1"), ("host_mute", "u1"), ("volume_8_8", "<i2")])
+assert DYNAMICS_CONFIG.itemsize == 48

@@ -64,3 +64,96 @@ def gather_rows(mine, total_rows, root=0):
     for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine.contiguous(), root)]):
         q.wait()
     return None
+
+
+def chunk_ranges(n_rows, n_chunks, unit=64):
+    """Row ranges [(lo, hi), ...] of one shard: at most `n_chunks` pieces on `unit`-row boundaries."""
+    per = -(-n_rows // max(1, n_chunks))
+    per = max(unit, -(-per // unit) * unit)
+    return [(lo, min(n_rows, lo + per)) for lo in range(0, n_rows, per)]
+
+
+def pipelined_scatter_process_gather(full, total_rows, row_len, dtype, device, process_range, n_chunks=8, root=0,
+                                     compute_stream=None):
+    """Frames originate on `root` ([total_rows, row_len]); every rank processes its contiguous shard and the results
+    land back in `full` on root - chunked and software-pipelined:
+
+        step j:   one grouped NCCL launch carries chunk j root -> peers AND chunk j-2 peers -> root (both NVLink
+                  directions busy), while every rank's kernel works on chunk j-1.
+
+    ``process_range(shard, lo, hi)`` enqueues the processing of rows [lo, hi) of the rank's shard tensor, in place
+    (asynchronous on ``compute_stream`` for CUDA tensors, synchronous on CPU).  Returns the rank's shard tensor
+    (root: a view of its rows of `full`).  Sharding and chunking change no bit of the result."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lo, hi = shard_range(total_rows, rank, world)
+    cuda = torch.device(device).type == "cuda"
+    if rank == root:
+        mine = full[lo:hi]
+    else:
+        mine = torch.empty((hi - lo, row_len), dtype=dtype, device=device)
+    ranges = {r: chunk_ranges(shard_range(total_rows, r, world)[1] - shard_range(total_rows, r, world)[0], n_chunks) for r in range(world)}
+    K = max(len(v) for v in ranges.values())
+    comm = torch.cuda.Stream(device=device) if cuda else None
+    comp = compute_stream
+    ev_recv = [torch.cuda.Event() for _ in range(K)] if cuda else None
+    ev_done = [torch.cuda.Event() for _ in range(K)] if cuda else None
+    if cuda:
+        comm.wait_stream(torch.cuda.current_stream(device))          # `full` / `mine` are ready
+
+    def compute(j):
+        mr = ranges[rank]
+        if j >= len(mr):
+            return
+        if cuda:
+            comp.wait_event(ev_recv[j])
+        process_range(mine, mr[j][0], mr[j][1])
+        if cuda:
+            ev_done[j].record(comp)
+
+    if world == 1 or rank == root:
+        # the root's own rows need no transfer: its kernel runs beside the transfers
+        if cuda:
+            comp.wait_stream(torch.cuda.current_stream(device))
+        for a, b in ranges[rank]:
+            process_range(mine, a, b)
+        if world == 1:
+            if cuda:
+                torch.cuda.current_stream(device).wait_stream(comp)
+            return mine
+    for j in range(K + 2):
+        ops = []
+        if rank == root:
+            for r in range(world):
+                if r == root:
+                    continue
+                base = shard_range(total_rows, r, world)[0]
+                rr = ranges[r]
+                if j < len(rr):
+                    ops.append(dist.P2POp(dist.isend, full[base + rr[j][0]:base + rr[j][1]], r))
+                if 0 <= j - 2 < len(rr):
+                    ops.append(dist.P2POp(dist.irecv, full[base + rr[j - 2][0]:base + rr[j - 2][1]], r))
+        else:
+            mr = ranges[rank]
+            if j < len(mr):
+                ops.append(dist.P2POp(dist.irecv, mine[mr[j][0]:mr[j][1]], root))
+            if 0 <= j - 2 < len(mr):
+                if cuda:
+                    comm.wait_event(ev_done[j - 2])                   # results of chunk j-2 are complete
+                ops.append(dist.P2POp(dist.isend, mine[mr[j - 2][0]:mr[j - 2][1]], root))
+        if ops:
+            if cuda:
+                with torch.cuda.stream(comm):
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                    if rank != root and j < len(ranges[rank]):
+                        ev_recv[j].record(comm)
+            else:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        if rank != root:
+            compute(j)                                               # chunk j: its kernel overlaps the next step's transfers
+    if cuda:
+        cur = torch.cuda.current_stream(device)
+        cur.wait_stream(comm)
+        cur.wait_stream(comp)
+    return mine

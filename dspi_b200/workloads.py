@@ -30,6 +30,30 @@ def xorshift_s16(C, T, ch0=0):
     return out
 
 
+def inputs_device(C, T, n_blocks, q28, device, ch0=0):
+    """The same per-channel xorshift32 streams generated on the GPU (torch, int64 lanes emulating uint32): returns
+    ``n_blocks`` tensors [C, T], block b holding frames [b*T, (b+1)*T) of every channel's stream - float32
+    ``s16 / 65536`` or int32 ``s16 << 13`` like :func:`inputs_f32` / :func:`inputs_q28` (bit-identical to them)."""
+    import torch
+    mask = 0xFFFFFFFF
+    st = (torch.arange(C, dtype=torch.int64, device=device) + int(ch0)) ^ int(XORSHIFT_SEED)
+    st = torch.where(st == 0, torch.ones_like(st), st)
+    blocks = []
+    for _ in range(n_blocks):
+        raw = torch.empty((T, C), dtype=torch.int16, device=device)
+        for t in range(T):
+            st = st ^ ((st << 13) & mask)
+            st = st ^ (st >> 17)
+            st = st ^ ((st << 5) & mask)
+            raw[t] = (st >> 16).to(torch.int16)             # wraps like the uint16 -> int16 view on the host
+        s16 = raw.t().contiguous()
+        if q28:
+            blocks.append(s16.to(torch.int32) << 13)
+        else:
+            blocks.append(s16.to(torch.float32) / 65536.0)
+    return blocks
+
+
 def inputs_f32(C, T, ch0=0):
     """float32 [C, T] uniform in [-0.5, 0.5): s16 / 65536 (exact in float)."""
     return (xorshift_s16(C, T, ch0).astype(np.float32) / np.float32(65536.0)).astype(np.float32)

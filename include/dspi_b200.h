@@ -146,6 +146,10 @@ int dspi_eq_set_params_device(dspi_eq *e, uint32_t ch0, uint32_t n, dspi_eq_para
  * Equivalent reference loop: for each channel, dsp_process_channel_block(
  * filters[ch], samples[ch], T, ch) — packet size does not change the values. */
 int dspi_eq_process_device(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld);
+/* The same for channels [ch0, ch0 + n) only: d_rows points at the row of channel ch0 ([n][ld], device memory); ch0 must be a
+ * multiple of 64.  For callers that stream a large block through in pieces (dspi_b200/sharding.py pipelines NCCL transfers
+ * against it).  Asynchronous on the engine's stream. */
+int dspi_eq_process_device_range(dspi_eq *e, void *d_rows, uint32_t T, uint32_t ld, uint32_t ch0, uint32_t n);
 int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T);
 int dspi_eq_sync(dspi_eq *e);
 /* cudaStream_t of the engine (so callers can order their own work / events) */
@@ -157,6 +161,35 @@ uint64_t dspi_eq_launch_count(dspi_eq *e);
  * vector get a kernel compiled for that vector at run time (NVRTC); this call triggers that
  * compilation if it is pending.  Results never depend on the choice.  No reference counterpart. */
 int dspi_eq_kernel_info(dspi_eq *e, char *buf, size_t cap);
+
+/* ---- EQ engine over several GPUs of one box, one process (SURVEY 8b `devices[], n_devices`, 8e) ------ */
+/* Channels shard into contiguous ranges, one per listed device (dspi_eqx_shard_range: 64-channel boundaries); all
+ * coefficients and filter state of a range stay on its owner and no data is exchanged between devices - the firmware's
+ * own two-core split is the same idea (disjoint output ranges, config.h:350-357).  Results are bit-identical to a
+ * single engine over all channels.  upload / download address channels of the whole group. */
+#define DSPI_MAX_DEVICES 8
+typedef struct dspi_eqx dspi_eqx;
+typedef struct {
+    uint32_t arith;                     /* DSPI_ARITH_*                                     */
+    uint32_t n_channels;                /* over the whole group                             */
+    uint32_t n_bands;
+    uint32_t n_devices;                 /* 1..DSPI_MAX_DEVICES                              */
+    int32_t  devices[DSPI_MAX_DEVICES]; /* CUDA ordinals; devices[0] is the root            */
+    uint32_t flags;                     /* 0                                                */
+} dspi_eqx_desc;
+int dspi_eqx_create(dspi_eqx **out, const dspi_eqx_desc *desc);
+int dspi_eqx_destroy(dspi_eqx *x);
+int dspi_eqx_shard_range(uint32_t n_channels, uint32_t n_devices, uint32_t k, uint32_t *lo, uint32_t *hi);
+int dspi_eqx_upload_biquads(dspi_eqx *x, uint32_t ch0, uint32_t n, const void *biquads);
+int dspi_eqx_download_biquads(dspi_eqx *x, uint32_t ch0, uint32_t n, void *biquads);
+/* samples [n_channels][T] in HOST memory (pinned: dspi_host_alloc): every device runs its staged PCIe pipeline on its
+ * rows concurrently; returns when all rows are back. */
+int dspi_eqx_process_host(dspi_eqx *x, void *h_samples, uint32_t T);
+/* samples [n_channels][T] resident on devices[0]: the root processes its rows in place, the other devices pull theirs
+ * over NVLink (peer access), process and push them back, chunked so that transfers in both directions overlap the
+ * kernels.  Returns when the block on the root is complete. */
+int dspi_eqx_process_root(dspi_eqx *x, void *d_samples_on_root, uint32_t T, uint32_t ld);
+uint64_t dspi_eqx_launch_count(dspi_eqx *x);
 
 /* ---- full signal chain: many independent DSPi device instances ------------------------------ */
 /* One instance = process_audio_packet() of one RP2350-shape device (usb_audio.c:500-1317, float
@@ -274,6 +307,23 @@ int dspi_chain_reset_state(dspi_chain *c);
  * fade runs across the packets of one call and across calls.  Arm a mute with dspi_preset_mute_arm() as the firmware's
  * flash operations do.  states == NULL leaves envelope mode: the constant preset_mute_gain of dspi_chain_set_params
  * applies again.  _get_ returns the current state (it is part of the state blob too). */
+/* Mass reconfiguration of the dynamics stages ON THE GPU: per instance what the firmware's main loop does
+ * when crossfeed_update_pending / leveller_update_pending / loudness_recompute_pending are set (main.c:868-895) -
+ * crossfeed_compute_coefficients() (crossfeed.c:35-127: new coefficients, filter state cleared), leveller_compute_coefficients()
+ * (leveller.c:42-89), loudness_recompute_table() (loudness.c:169-217) for the row audio_set_volume() selects - followed by
+ * audio_set_volume() (usb_audio.c:428-440): the host volume becomes vol_mul (the int16 quirk included) and the output gains
+ * follow.  cfgs[n] is host memory.  Arithmetic and libm policy as dspi_eq_set_params_device.  The bypass flags, preamp,
+ * master volume, matrix and delays stay as dspi_chain_set_params left them. */
+typedef struct {
+    dspi_crossfeed_config crossfeed;     /* crossfeed_config, usb_audio.c:187-193                       */
+    dspi_leveller_config  leveller;      /* leveller_config, usb_audio.c:199-206                        */
+    float   loudness_ref_spl;            /* loudness_ref_spl, usb_audio.c:175                           */
+    float   loudness_intensity_pct;      /* loudness_intensity_pct, usb_audio.c:176                     */
+    uint8_t loudness_enabled;            /* loudness_enabled, usb_audio.c:174                           */
+    uint8_t host_mute;                   /* audio_state.mute                                            */
+    int16_t volume_8_8;                  /* audio_state.volume: UAC1 volume in 1/256 dB, 0 = full scale */
+} dspi_dynamics_config;
+int dspi_chain_set_dynamics_device(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_dynamics_config *cfgs, float sample_rate);
 int dspi_chain_set_preset_mute(dspi_chain *c, uint32_t inst0, uint32_t n, const dspi_preset_mute *states, uint32_t sample_rate_hz);
 int dspi_chain_get_preset_mute(dspi_chain *c, uint32_t inst0, uint32_t n, dspi_preset_mute *states);
 /* Checkpoint / resume (the dspi_state_export/import of SURVEY 8 b): everything a later process call depends on besides
@@ -299,6 +349,11 @@ int dspi_chain_process_device(dspi_chain *c, const void *d_pcm, uint32_t bit_dep
 int dspi_chain_sync(dspi_chain *c);
 void *dspi_chain_stream(dspi_chain *c);
 uint64_t dspi_chain_launch_count(dspi_chain *c);
+/* How the engine split the GPU for this chain: the delta-sigma modulator (one serial chain per instance, latency-bound)
+ * runs alone on pdm_sms SMs, every other stage on rest_sms (CUDA green contexts; 0 / 0 when the driver offers none or
+ * DSPI_PDM_SMS=0 is set - results never depend on it).  No reference counterpart: the firmware gives the modulator
+ * core 1 (pdm_generator.c:691-721). */
+int dspi_chain_sm_partition(dspi_chain *c, uint32_t *pdm_sms, uint32_t *rest_sms);
 /* dsp_update_delay_samples() for one output, dsp_pipeline.c:216-239 (is_last adds SUB_ALIGN_SAMPLES) */
 int32_t dspi_delay_samples(float delay_ms, float sample_rate, int is_last);
 
@@ -351,6 +406,7 @@ int dspi_chainq_upload_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, const
 int dspi_chainq_download_biquads(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_biquad_q28 *biquads);
 int dspi_chainq_set_eq_params_device(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_eq_param *recipes, float sample_rate);   /* recipes[n][7][12] */
 int dspi_chainq_reset_state(dspi_chainq *c);
+int dspi_chainq_set_dynamics_device(dspi_chainq *c, uint32_t inst0, uint32_t n, const dspi_dynamics_config *cfgs, float sample_rate);
 int dspi_chainq_set_preset_mute(dspi_chainq *c, uint32_t inst0, uint32_t n, const dspi_preset_mute *states, uint32_t sample_rate_hz);   /* Q15 use of the gain: usb_audio.c:976-980 */
 int dspi_chainq_get_preset_mute(dspi_chainq *c, uint32_t inst0, uint32_t n, dspi_preset_mute *states);
 size_t dspi_chainq_state_size(dspi_chainq *c);
@@ -362,7 +418,9 @@ int dspi_chainq_process_host(dspi_chainq *c, const void *pcm, uint32_t bit_depth
 int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_depth, uint32_t n_packets, uint32_t frames_per_packet,
                                int32_t *d_spdif_out, uint32_t *d_pdm_out, dspi_status_q28 *d_status);
 int dspi_chainq_sync(dspi_chainq *c);
+void *dspi_chainq_stream(dspi_chainq *c);
 uint64_t dspi_chainq_launch_count(dspi_chainq *c);
+int dspi_chainq_sm_partition(dspi_chainq *c, uint32_t *pdm_sms, uint32_t *rest_sms);
 /* Q28 stores of the crossfeed and loudness parameter functions (crossfeed.c:116-119, loudness.c:131-162) */
 void dspi_crossfeed_compute_coefficients_q28(dspi_crossfeed_state_q28 *st, const dspi_crossfeed_config *cfg, float sample_rate);
 void dspi_loudness_compute_table_q28(dspi_loudness_coeffs_q28 table[61][2], float ref_spl, float intensity_pct, float sample_rate);
@@ -475,6 +533,10 @@ int dspi_spdif_encode_host(int device, const int32_t *words, uint64_t n_streams,
 /* pinned host memory helpers */
 void *dspi_host_alloc(size_t bytes);
 void dspi_host_free(void *p);
+/* Bind the calling thread - and the memory it allocates from now on - to the NUMA node of the device's PCIe link
+ * (sysfs numa_node + sched_setaffinity + set_mempolicy), so that staging memory allocated afterwards is local to the
+ * link.  Returns the node, or -1 when the topology is not exposed (nothing changed).  Call before dspi_host_alloc. */
+int dspi_bind_host_to_device(int device);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,8 @@ static inline float orc_log10f(float x)
 static inline float orc_sinf(float x) { return orc_libm_f64_mode ? (float)sin((double)x) : sinf(x); }
 static inline float orc_cosf(float x) { return orc_libm_f64_mode ? (float)cos((double)x) : cosf(x); }
 static inline float orc_tanf(float x) { return orc_libm_f64_mode ? (float)tan((double)x) : tanf(x); }
+static inline float orc_expf(float x) { return orc_libm_f64_mode ? (float)exp((double)x) : expf(x); }
+static inline float orc_logf(float x) { return orc_libm_f64_mode ? (float)log((double)x) : logf(x); }
 static inline float orc_powf(float a, float b)
 {
     return orc_libm_f64_mode ? (float)pow((double)a, (double)b) : powf(a, b);

@@ -151,9 +151,9 @@ static int xfeed_core(const orc_xfeed_cfg *cfg, float fs, float *lp_a0, float *l
         if (feed_db < 0.0f) feed_db = 0.0f;
         if (feed_db > 15.0f) feed_db = 15.0f;
     }
-    float level_ratio = powf(10.0f, feed_db / 20.0f);                    /* :67 */
+    float level_ratio = orc_powf(10.0f, feed_db / 20.0f);                    /* :67 */
     float G = 1.0f / (1.0f + level_ratio);
-    float x = expf(-2.0f * ORC_PI * fc / fs);                            /* :75 */
+    float x = orc_expf(-2.0f * ORC_PI * fc / fs);                            /* :75 */
     *lp_a0 = G * (1.0f - x);
     *lp_b1 = x;
     if (cfg->itd_enabled) {                                              /* :98-109 */
@@ -188,7 +188,7 @@ void orc_xfeed_coeffs_q28(orc_xfeed_q28 *st, const orc_xfeed_cfg *cfg, float fs)
 static float lev_alpha(float fs, float t)
 {
     if (t <= 0.0f || fs <= 0.0f) return 0.0f;
-    return expf(-logf(10.0f) / (fs * t));
+    return orc_expf(-orc_logf(10.0f) / (fs * t));
 }
 
 void orc_lev_coeffs_compute(orc_lev_coeffs *out, const orc_lev_cfg *cfg, float fs)
@@ -234,11 +234,11 @@ void orc_lev_reset_q28(orc_lev_state_q28 *st)
 /* loudness.c:37-50 */
 static float iso226_spl(float Tf, float af, float Lu, float phon)
 {
-    float B = 0.4f * powf(10.0f, (Tf + Lu) / 10.0f - 9.0f);
-    float threshold = powf(B, af);
-    float Af = 4.47e-3f * (powf(10.0f, 0.025f * phon) - 1.15f) + threshold;
+    float B = 0.4f * orc_powf(10.0f, (Tf + Lu) / 10.0f - 9.0f);
+    float threshold = orc_powf(B, af);
+    float Af = 4.47e-3f * (orc_powf(10.0f, 0.025f * phon) - 1.15f) + threshold;
     if (Af < 1e-10f) Af = 1e-10f;
-    return (10.0f / af) * log10f(Af) - Lu + 94.0f;
+    return (10.0f / af) * orc_log10f(Af) - Lu + 94.0f;
 }
 /* loudness.c:54-78 */
 static float loud_comp_db(float Tf, float af, float Lu, float ref_spl, float eff_phon, float intensity)
@@ -262,8 +262,8 @@ static void shelf_f32(float freq, float Q, float gain_db, int high, float fs, or
         return;
     }
     o->bypass = 0;
-    float A = powf(10.0f, gain_db / 40.0f);
-    float g = tanf(ORC_PI * freq / fs);
+    float A = orc_powf(10.0f, gain_db / 40.0f);
+    float g = orc_tanf(ORC_PI * freq / fs);
     float sqrtA = sqrtf(A);
     if (high) g = g * sqrtA; else g = g / sqrtA;
     float k = 1.0f / Q;
@@ -282,9 +282,9 @@ static void shelf_q28(float freq, float Q, float gain_db, int high, float fs, or
         return;
     }
     o->bypass = 0;
-    float A = powf(10.0f, gain_db / 40.0f);
+    float A = orc_powf(10.0f, gain_db / 40.0f);
     float omega = 2.0f * ORC_PI * freq / fs;
-    float sn = sinf(omega), cs = cosf(omega);
+    float sn = orc_sinf(omega), cs = orc_cosf(omega);
     float alpha = sn / (2.0f * Q);
     float sqrtA = sqrtf(A);
     float a0, a1, a2, b0, b1, b2;

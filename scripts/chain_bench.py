@@ -54,5 +54,5 @@ else:
     e1.record(st)
     eng.sync()
     ms = e0.elapsed_time(e1) / a.reps
-print(json.dumps({"instances": N, "frames": F, "ms_per_step": ms, "instance_frames_per_s": N * F / (ms * 1e-3),
+print(json.dumps({"instances": N, "frames": F, "sm_partition": eng.sm_partition(), "ms_per_step": ms, "instance_frames_per_s": N * F / (ms * 1e-3),
                   "arith": a.arith, "output_channel_samples_per_s": N * n_out * F / (ms * 1e-3), "realtime_factor": (F / fs) / (ms * 1e-3)}))
