@@ -406,15 +406,10 @@ def main():
             full = torch.rand((total, T), dtype=torch.float32, device="cuda") - 0.5 if not q else \
                 torch.randint(-2**27, 2**27, (total, T), dtype=torch.int32, device="cuda")
         dt_t = torch.int32 if q else torch.float32
-        comp = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
-
-        def process_range(shard, a, b):            # rows [a, b) of this rank's shard, in place, asynchronous on the engine stream
-            eng.process_device_range(shard[a:b].data_ptr(), T, T, a, b - a)
+        sg = sharding.native_scatter_gather(eng, local_rank)       # dspi_sg_*: NCCL send / recv issued from the C library
 
         def sg_step():
-            sharding.pipelined_scatter_process_gather(full, total, T, dt_t, torch.device("cuda", local_rank), process_range, n_chunks=8,
-                                                      compute_stream=comp)
-            torch.cuda.current_stream().synchronize()
+            sg.process(full.data_ptr() if rank == 0 else 0, total, T, 0)      # 0: chunk count chosen by the library
         sg_step()
         dist.barrier()
         torch.cuda.synchronize()
@@ -426,9 +421,10 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         nccl = {"value": float(total) * T * n_sg / float(dt.item()), "unit": "samples/s", "steps": n_sg,
-                "path": "rank 0 holds all frames: 8 row chunks per shard, one grouped NCCL send/recv launch per step carries chunk j out and chunk j-2 back while the kernels work on chunk j-1 (sharding.pipelined_scatter_process_gather)",
+                "path": "rank 0 holds all frames: dspi_sg_process - row chunks (count chosen from transfer / kernel time), one NCCL group per step carries chunk j out and chunk j-2 back while the kernels work on chunk j-1",
                 "bytes_over_nvlink_per_step": int(total - Cn) * T * 4 * 2}
         del full
+        sg.close()
 
     other = None
     if rank == 0 and world == 1 and not args.no_extras:

@@ -35,6 +35,7 @@ SYMBOLS = [
     "dspi_bulk_state_defaults", "dspi_bulk_params_apply", "dspi_bulk_params_collect", "dspi_bulk_state_to_chain_f32", "dspi_bulk_state_to_chain_q28",
     "dspi_preset_slot_size", "dspi_crc32", "dspi_preset_slot_apply", "dspi_preset_slot_collect",
     "dspi_preamp", "dspi_master_volume", "dspi_preset_mute_arm", "dspi_preset_mute_step",
+    "dspi_nccl_unique_id", "dspi_sg_create", "dspi_sg_destroy", "dspi_sg_process",
     "dspi_chainq_stream", "dspi_eq_process_device_range", "dspi_bind_host_to_device", "dspi_eqx_create", "dspi_eqx_destroy", "dspi_eqx_shard_range",
     "dspi_eqx_upload_biquads", "dspi_eqx_download_biquads", "dspi_eqx_process_host", "dspi_eqx_process_root", "dspi_eqx_launch_count",
     "dspi_chain_set_dynamics_device", "dspi_chainq_set_dynamics_device", "dspi_chain_sm_partition", "dspi_chainq_sm_partition",
@@ -137,6 +138,10 @@ def lib():
             getattr(h, pre + "_sm_partition").argtypes = [vp, vp, vp]
         h.dspi_eq_process_device_range.argtypes = [vp, vp, u32, u32, u32, u32]
         h.dspi_bind_host_to_device.argtypes = [C.c_int]
+        h.dspi_nccl_unique_id.argtypes = [vp]
+        h.dspi_sg_create.argtypes = [C.POINTER(vp), vp, C.c_int, vp, C.c_int, C.c_int, C.c_int]
+        h.dspi_sg_destroy.argtypes = [vp]
+        h.dspi_sg_process.argtypes = [vp, vp, u32, u32, u32]
         h.dspi_eqx_create.argtypes = [C.POINTER(vp), C.POINTER(_EqxDesc)]
         h.dspi_eqx_destroy.argtypes = [vp]
         h.dspi_eqx_shard_range.argtypes = [u32, u32, u32, vp, vp]
@@ -320,6 +325,31 @@ class EqGroup:
     @property
     def launch_count(self):
         return int(lib().dspi_eqx_launch_count(self._h))
+
+
+def nccl_unique_id():
+    """128-byte NCCL unique id (call on one rank, hand the bytes to the others)."""
+    buf = (C.c_uint8 * 128)()
+    _check(lib().dspi_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+class ScatterGather:
+    """One rank's end of the native NCCL scatter / process / gather pipeline (``dspi_sg_*``) around an :class:`EqEngine`."""
+
+    def __init__(self, engine, device, unique_id, rank, world, root=0):
+        self._h = C.c_void_p()
+        self.engine = engine
+        idb = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(lib().dspi_sg_create(C.byref(self._h), engine._h, int(device), idb, int(rank), int(world), int(root)))
+
+    def process(self, full_ptr, total_channels, T, n_chunks=0):
+        _check(lib().dspi_sg_process(self._h, C.c_void_p(int(full_ptr)) if full_ptr else None, int(total_channels), int(T), int(n_chunks)))
+
+    def close(self):
+        if self._h:
+            lib().dspi_sg_destroy(self._h)
+            self._h = C.c_void_p()
 
 
 def bind_host_to_device(device):

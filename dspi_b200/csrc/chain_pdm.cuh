@@ -34,32 +34,36 @@ __device__ __forceinline__ void pdm_modulate_frames(int32_t *__restrict__ pdm, c
             const int32_t in = raw - err_acc;
             const int32_t dither = (15778 * in - 31556 * x1 + 15778 * x2 + 31531 * y1 - 15580 * y2) >> 14;   // :98-99
             x2 = x1; x1 = in; y2 = y1; y1 = dither;
-            // :372-378 restated on two running sums so that only TWO dependent integer ops separate
-            // consecutive decisions (the loop is one serial chain per instance, so its depth is the cost):
-            //   s = err2 + dither   (the comparator input)       g = err1 + target
-            //   bit = s >= 0;  s' = s + g - 2*fb;  g' = g + target - fb        (fb = bit ? 65535 : 0)
-            // which is err1 += target - fb; err2 += err1 - fb with the substitutions above (all int32,
-            // wrapping like the reference).  With m = s >> 31 (0 when the bit is 1, -1 when it is 0) the
-            // corrections become m * -K + (sum - K): one shift on the ALU pipe feeding one IMAD on the
-            // FMA pipe per decision.  Measured on B200 with one warp per SM sub-partition
-            // (scripts/pdm_ubench.cu): 13.5 cycles per decision against 18.0 for the mask form,
-            // 20.4 with predicated corrections, 23.4 for the reference's own statement order.
+            // :372-378 restated on three running sums so that only TWO dependent integer ops separate consecutive
+            // decisions and neither waits for a late operand (the loop is one serial chain per instance, its depth is the cost):
+            //   s = err2 + dither (the comparator input)   g = err1 + target
+            //   bit = s >= 0;   s' = s + g - 2*fb;   g' = g + target - fb        (fb = bit ? K : 0, K = 65535)
+            // which is err1 += target - fb; err2 += err1 - fb with the substitutions above (all int32, wrapping like the
+            // reference).  With m = s >> 31 (0 when the bit is 1, -1 when it is 0), t2 = s + g - 2K and g2 = g + target - K:
+            //   s' = m * -2K + t2      t2' = s' + g' - 2K = m * -3K + (t2 + g2 - 2K)      g2' = g' + target - K = m * -K + (g2 + target - K)
+            // Every addend on the right depends on the PREVIOUS step only, so a decision is one shift (ALU pipe) feeding
+            // three independent IMADs (FMA pipe).  Cycles per decision, one warp per SM sub-partition on B200
+            // (scripts/pdm_ubench.cu, profiles/r2_ubench_pdm.txt): 11.9 for this form, 13.5 for two sums (s' and g' feed an
+            // add before the next IMAD), 15.2 for an fp32 formulation (saturating add as comparator), 18.0 for the mask
+            // form, 20.4 with predicated corrections, 23.4 for the reference's own statement order.
             uint32_t inv = 0;                                                // complement of the output word
             int32_t s = err2 + dither;
-            int32_t g = err1 + target;
             const int32_t tg = target - 65535;
+            int32_t g2 = err1 + target + tg;
+            int32_t t2 = s + g2 - 65535 - target;                            // s + g - 2K with g = g2 - tg
 #pragma unroll
             for (int k = 0; k < 32; k++) {
                 const int32_t m = s >> 31;
-                const int32_t t2 = s + g - 2 * 65535;
-                const int32_t g2 = g + tg;
+                const int32_t a = t2 + g2 - 2 * 65535;
+                const int32_t b = g2 + tg;
                 inv = __funnelshift_l((uint32_t)s, inv, 1);                  // shift the sign in, MSB first (:375)
                 s = m * (-2 * 65535) + t2;
-                g = m * -65535 + g2;
+                t2 = m * (-3 * 65535) + a;
+                g2 = m * -65535 + b;
             }
             const uint32_t word = ~inv;
             err2 = s - dither;
-            err1 = g - target;
+            err1 = g2 - tg - target;
             words[chunk] = word;
         }
         err1 -= err1 >> 16;                                                  // :396-397

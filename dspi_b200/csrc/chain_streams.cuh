@@ -65,9 +65,12 @@ struct ChainStreams {
     {
         int n = 0;
         bounds[0] = 0;
-        const char *uni = getenv("DSPI_UNIFORM_SLICES");
-        if (uni && uni[0] == '1') {
-            const uint32_t k = n_packets < 8u ? n_packets : 8u;
+        const char *uni = getenv("DSPI_UNIFORM_SLICES");                // "1": eight equal slices; "n": n equal slices (<= 16)
+        if (uni && uni[0] >= '1' && uni[0] <= '9') {
+            uint32_t want = (uint32_t)atoi(uni);
+            if (want == 1u) want = 8u;
+            if (want > (uint32_t)kMaxSlices) want = (uint32_t)kMaxSlices;
+            const uint32_t k = n_packets < want ? n_packets : want;
             for (uint32_t i = 1; i <= k; i++) bounds[i] = (uint32_t)((uint64_t)n_packets * i / k);
             return (int)k;
         }

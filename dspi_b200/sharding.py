@@ -11,12 +11,12 @@ import torch.distributed as dist
 
 
 def shard_range(total, rank, world):
-    """Contiguous range [lo, hi) of `total` rows owned by `rank`; sizes differ by at most one and
-    every boundary is a multiple of 64 channels when total is (one warp group never straddles ranks)."""
-    unit = 64 if total % (64 * world) == 0 else 1
-    n = total // unit
-    lo = (n * rank) // world * unit
-    hi = (n * (rank + 1)) // world * unit
+    """Contiguous range [lo, hi) of `total` rows owned by `rank`: 64-row units (one warp group of K1 never straddles two
+    ranks) dealt out evenly - the same arithmetic as dspi_eqx_shard_range() in the C library."""
+    unit = 64
+    units = (total + unit - 1) // unit
+    lo = min(total, units * rank // world * unit)
+    hi = min(total, units * (rank + 1) // world * unit)
     return lo, hi
 
 
@@ -157,3 +157,15 @@ def pipelined_scatter_process_gather(full, total_rows, row_len, dtype, device, p
         cur.wait_stream(comm)
         cur.wait_stream(comp)
     return mine
+
+
+def native_scatter_gather(engine, device_index, root=0):
+    """The native pipeline (dspi_b200/csrc/nccl_sg.cu: NCCL calls issued from the C library, no Python in the loop) for
+    the ranks of the default process group.  The engine of rank r must hold the channels
+    ``shard_range(total, r, world)``.  Returns an ``api.ScatterGather``; call ``.process(full.data_ptr() or 0, total, T)``
+    on every rank."""
+    from dspi_b200 import api
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [api.nccl_unique_id() if rank == root else None]
+    dist.broadcast_object_list(box, src=root)
+    return api.ScatterGather(engine, device_index, box[0], rank, world, root)

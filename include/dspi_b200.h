@@ -191,6 +191,20 @@ int dspi_eqx_process_host(dspi_eqx *x, void *h_samples, uint32_t T);
 int dspi_eqx_process_root(dspi_eqx *x, void *d_samples_on_root, uint32_t T, uint32_t ld);
 uint64_t dspi_eqx_launch_count(dspi_eqx *x);
 
+/* ---- one rank per GPU: frames that originate on one rank, over NCCL ------------------------- */
+/* Multi-PROCESS form of dspi_eqx_process_root: every rank owns an EQ engine over its shard
+ * [lo_r, hi_r) = dspi_eqx_shard_range(total, world, r); the block [total][T] lives on the root rank.  dspi_sg_process
+ * scatters it in row chunks with grouped ncclSend / ncclRecv, runs the engines on chunk j-1 while chunk j travels out and
+ * chunk j-2 travels back in the same NCCL group (both NVLink directions busy), and leaves the results in the root's block.
+ * n_chunks = 0 lets the library choose (a cascade kernel takes as long as its rows are long however few rows it gets, so
+ * more chunks only pay while one chunk's transfer still outlasts a kernel).  libnccl.so.2 is dlopen'ed at first use.  The 128-byte unique id comes from dspi_nccl_unique_id() on one rank and is
+ * handed to the others by the caller (dspi_b200/sharding.py broadcasts it with torch.distributed). */
+typedef struct dspi_sg dspi_sg;
+int dspi_nccl_unique_id(void *id128);
+int dspi_sg_create(dspi_sg **out, dspi_eq *engine, int device, const void *id128, int rank, int world, int root);
+int dspi_sg_destroy(dspi_sg *g);
+int dspi_sg_process(dspi_sg *g, void *d_full_on_root, uint32_t total_channels, uint32_t T, uint32_t n_chunks);
+
 /* ---- full signal chain: many independent DSPi device instances ------------------------------ */
 /* One instance = process_audio_packet() of one RP2350-shape device (usb_audio.c:500-1317, float
  * pipeline :560-967, single-core branch :874-960): 2 inputs -> preamp -> loudness -> master EQ ->

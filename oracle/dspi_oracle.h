@@ -10,14 +10,18 @@
  * (WeebLabs/DSPi, /root/reference/firmware/DSPi) for the hot path of
  * SURVEY.md §8(a).  Every function cites the reference file:line it follows.
  *
- * Pinning status: the reference ships NO golden vectors or tests for this
- * path, so the restatement is pinned against the reference's
- * own sources compiled on the host (the libraries under oracle/_ref/, see oracle/Makefile and
- * tests/test_oracle_vs_ref.py) and against committed fixtures generated from
- * those builds (tests/golden/).  The orchestrator glue of usb_audio.c and the
- * Thumb assembly cannot be compiled on x86; those parts are pinned only by
- * cross-checks against the compiled pieces they call ("parity unpinned" for
- * the glue itself — stated again in DESIGN.md).
+ * Pinning status: the reference ships NO golden vectors or tests for this path, so the
+ * restatement is pinned against the reference's OWN sources compiled on the host (oracle/_ref/, see
+ * oracle/Makefile), bit for bit:
+ *   - dsp_pipeline.c, crossfeed.c, leveller.c, loudness.c unmodified (ref_shim.c)      tests/test_oracle_vs_ref.py
+ *   - usb_audio.c unmodified: process_audio_packet(), the whole per-packet orchestrator, both platform builds,
+ *     float strict + fused (ref_chain_shim.c, SDK platform layer in stubs_fw/)          tests/test_chain_vs_ref_cpu.py
+ *   - pdm_generator.c unmodified: the delta-sigma loop entered through pdm_core1_entry() (ref_pdm_shim.c)
+ *   - bulk_params.c, flash_storage.c, sample_encoding.h for the "next" rows
+ * and against committed fixtures generated from those builds (tests/golden/).  What stays a restatement without a
+ * compiled counterpart: the Thumb-1 block cascade of dsp_process_rp2040.S (no ARM toolchain; restated from the listing
+ * and cross-checked against a loop around the reference's compiled fast_mul_q28) and the two ARMv8-M inline-asm blocks
+ * of the 24-bit unpack (usb_audio.c:613-674; restated instruction by instruction in ref_chain_shim.c).
  *
  * Three arithmetic flavours:
  *   f32 strict  — every multiply/add rounded separately (host gcc, no FMA)

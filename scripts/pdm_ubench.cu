@@ -82,6 +82,54 @@ __device__ __forceinline__ uint32_t chunk(int32_t &err1, int32_t &err2, int32_t 
         }
         word = ~inv;
         err2 = s - dither; err1 = g - target;
+    } else if constexpr (V == 6) {          // fp32: every quantity is an integer below 2^24 in magnitude (guarded), so float adds and
+                                            // fmas are exact; the comparator is one saturating add, the correction one fma: 2 dependent
+                                            // 4-cycle FMA-pipe ops per decision.  Falls back to the integer form when the guard trips.
+        const int32_t e1 = err1, e2 = err2;
+        float s = (float)(err2 + dither), g = (float)(err1 + target);
+        const float tf = (float)target;
+        float hi = 0.0f, lo = 0.0f, ms = fabsf(s), mg = fabsf(g);
+        bool ok = abs(err2 + dither) < (1 << 23) && abs(err1 + target) < (1 << 23);
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const float b = __saturatef(s + 1.0f);            // 1.0 when s >= 0 (s is an integer), else 0.0
+            const float t2 = s + g;
+            const float g2 = g + tf;
+            s = fmaf(b, -131070.0f, t2);
+            g = fmaf(b, -65535.0f, g2);
+            if (k < 16) hi = fmaf(hi, 2.0f, b); else lo = fmaf(lo, 2.0f, b);
+            ms = fmaxf(ms, fabsf(s));
+            mg = fmaxf(mg, fabsf(g));
+        }
+        ok = ok && ms < 8000000.0f && mg < 8000000.0f;        // every intermediate (s + g, g + target) stayed below 2^24
+        if (ok) {
+            word = ((uint32_t)hi << 16) | (uint32_t)lo;
+            err2 = (int32_t)s - dither; err1 = (int32_t)g - target;
+        } else {
+            err1 = e1; err2 = e2;
+            word = chunk<5>(err1, err2, target, dither);
+        }
+    } else if constexpr (V == 7) {          // three running sums: the addends of all three IMADs depend on the PREVIOUS step only, so the
+                                            // per-decision chain is IMAD -> SHF -> IMAD with no operand arriving late:
+                                            //   t2 = s + g - 2K,  g2 = g + target - K;   m = s >> 31
+                                            //   s' = m * -2K + t2;   t2' = m * -3K + (t2 + g2 - 2K);   g2' = m * -K + (g2 + target - K)
+        int32_t sv = err2 + dither;
+        const int32_t g0 = err1 + target, tg = target - 65535;
+        int32_t t2 = sv + g0 - 131070, g2 = g0 + tg;
+        uint32_t inv = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const int32_t m = sv >> 31;
+            const int32_t a = t2 + g2 - 131070;
+            const int32_t b = g2 + tg;
+            inv |= (uint32_t)m & (1u << (31 - k));
+            sv = m * -131070 + t2;
+            t2 = m * -196605 + a;
+            g2 = m * -65535 + b;
+        }
+        word = ~inv;
+        err2 = sv - dither;
+        err1 = g2 - tg - target;                               // g2 = g + tg, g = err1 + target
     }
     return word;
 }
@@ -175,6 +223,8 @@ int main()
         run<3>("imad two-sum", st, out, cyc, w);
         run<4>("select two-sum", st, out, cyc, w);
         run<5>("imad two-sum, lop3 word", st, out, cyc, w);
+        run<6>("fp32 saturating-add two-sum", st, out, cyc, w);
+        run<7>("imad three-sum", st, out, cyc, w);
     }
     return 0;
 }

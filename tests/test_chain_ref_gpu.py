@@ -369,3 +369,23 @@ def test_config3_full_instance_count_against_the_oracle(oracle, flavour):
     finally:
         eng.close()
         oracle.set_libm_f64(0)
+
+
+@pytest.mark.parametrize("flavour", ["f32s", "f32f", "q28"])
+def test_gpu_chain_against_the_committed_reference_vectors(flavour):
+    """tests/golden/chain.npz: outputs of the reference's own compiled orchestrator + modulator (no oracle involved)."""
+    from tests.util import load_golden
+    g = load_golden("chain.npz")
+    P, bq, pcm = g[f"{flavour}_params"], g[f"{flavour}_biquads"], g[f"{flavour}_pcm"]
+    npk, fpp = int(g["n_packets"]), int(g["fpp"])
+    eng = _engine(flavour, len(P), npk * fpp)
+    try:
+        eng.set_params(P)
+        eng.upload_biquads(bq)
+        spdif, pdm, status = eng.process_host(np.ascontiguousarray(pcm), 24, npk, fpp)
+        assert np.array_equal(spdif, g[f"{flavour}_spdif"])
+        assert np.array_equal(pdm, g[f"{flavour}_pdm"])
+        assert np.array_equal(status["peaks"], g[f"{flavour}_peaks"][:, :status["peaks"].shape[1]])
+        assert [int(s["clip_flags"]) for s in status] == [int(c) for c in g[f"{flavour}_clip"]]
+    finally:
+        eng.close()

@@ -44,3 +44,21 @@ def test_cfg1_known_answers():
     assert bq["use_svf"][0, 0] == 1 and bq["use_svf"][0, 1] == 1 and bq["use_svf"][0, 2] == 0   # 10 kHz >= 48k/7.5
     assert np.all(bq["bypass"][:, 3:] == 1) and np.all(bq["b0"][:, 3:] == 1.0)
     assert np.all(g["bq_q28"]["b0"][:, 3:] == 1 << 28)
+
+
+@pytest.mark.parametrize("flavour", ["f32s", "f32f", "q28"])
+def test_chain_fixture(oracle, flavour):
+    """Vectors made by the reference's own process_audio_packet() + modulator loop (tests/golden/make_golden_chain.py)."""
+    from tests.orc import make_orc_chain, make_orc_chain_q28, orc_chain_run, orc_chain_run_q28
+    g = load_golden("chain.npz")
+    P, bq, pcm = g[f"{flavour}_params"], g[f"{flavour}_biquads"], g[f"{flavour}_pcm"]
+    npk, fpp = int(g["n_packets"]), int(g["fpp"])
+    for i in range(len(P)):
+        if flavour == "q28":
+            ch = make_orc_chain_q28(oracle, P[i], bq[i])
+            sp, pdm = orc_chain_run_q28(oracle, ch, pcm[i], 24, npk, fpp)
+        else:
+            ch = make_orc_chain(oracle, P[i], bq[i])
+            sp, pdm = orc_chain_run(oracle, flavour, ch, pcm[i], 24, npk, fpp)
+        assert np.array_equal(sp, g[f"{flavour}_spdif"][i]) and np.array_equal(pdm, g[f"{flavour}_pdm"][i])
+        assert list(ch.peaks)[:g[f"{flavour}_peaks"].shape[1]] == list(g[f"{flavour}_peaks"][i]) and int(ch.clip_flags) == int(g[f"{flavour}_clip"][i])
