@@ -10,7 +10,7 @@
 // The chain is feed-forward between stages (nothing downstream feeds an upstream stage), so a call is
 // run stage by stage over whole slices of packets instead of packet by packet:
 //
-//   chain_pre_kernel      lane = instance: PCM unpack, preamp, the two loudness shelves; results leave
+//   chain_pre_kernel      warp = 16 instances x {L, R}: PCM unpack, preamp, the two loudness shelves; results leave
 //                         through a shared-memory transpose as ROWS [2 N][frames] (row = side * N + inst)
 //   K1 (eq_f32_kernel.cuh) the 10-band master EQ over those rows — the same TMA-fed packed-FFMA2 kernel
 //                         (and run-time specialisation) as the EQ engine, not a second implementation
@@ -108,42 +108,40 @@ template <bool FUSED>
 __global__ void __launch_bounds__(64)
 chain_pre_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t f_begin, uint32_t f_end, uint32_t F)
 {
-    __shared__ float tile_s[2][2][32][kXs];
-    __shared__ uint32_t pcm_s[2][2][32][49];              // per warp, double-buffered: 32 instances x 32 frames x <= 6 bytes (rows padded to 49 words)
+    // warp = 16 instances x {L, R}: lane l handles side l >> 4 of instance inst16 + (l & 15).  The two sides of an
+    // instance share nothing in this stage (separate shelf states, usb_audio.c:696 / :707), so splitting them over two
+    // lanes halves the serial chain per lane and doubles the warps of a stage that is latency-bound on few warps.
+    __shared__ float tile_s[2][32][kXs];                  // per warp: [frame][row = side * 16 + instance]
+    __shared__ uint32_t pcm_s[2][2][16][49];              // per warp, double-buffered: 16 instances x 32 frames x <= 6 bytes (rows padded to 49 words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t inst0 = (blockIdx.x * 2 + warp) * 32;
-    if (inst0 >= d.N_pad) return;
-    const uint32_t inst = inst0 + lane;
+    const uint32_t inst16 = (blockIdx.x * 2 + warp) * 16;
+    if (inst16 >= d.N_pad) return;
+    const uint32_t side = lane >> 4, li = lane & 15;
+    const uint32_t inst = inst16 + li;
     const bool live = inst < d.N;
     const uint32_t Np = d.N_pad;
-    float (*tile)[32][kXs] = tile_s[warp];
+    float (*tile)[kXs] = tile_s[warp];
 
     const bool loud_on = d.flags[inst] & F_LOUD;
     const uint8_t loud_byp = d.loud_byp[inst];
-    float lc[2][6], ls[2][2][2], gain_in[2];
+    float lc[2][6], ls[2][2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
 #pragma unroll
         for (int k = 0; k < 6; k++) lc[j][k] = d.loud_c[(j * 6 + k) * Np + inst];
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            ls[side][j][0] = d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst];
-            ls[side][j][1] = d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst];
-        }
+        ls[j][0] = d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst];
+        ls[j][1] = d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst];
     }
     const uint32_t bpf = bit_depth == 24 ? 6u : 4u;
-#pragma unroll
-    for (int side = 0; side < 2; side++) {
-        const float preamp = d.preamp[side * Np + inst];
-        gain_in[side] = bit_depth == 24 ? __fmul_rn(1.0f / 8388608.0f, preamp)       // usb_audio.c:601-603
-                                        : __fmul_rn(1.0f / 32768.0f, preamp);         // :680-681
-    }
+    const float preamp = d.preamp[side * Np + inst];
+    const float gain_in = bit_depth == 24 ? __fmul_rn(1.0f / 8388608.0f, preamp)        // usb_audio.c:601-603
+                                          : __fmul_rn(1.0f / 32768.0f, preamp);          // :680-681
     // Each instance's packet stream is contiguous ([inst][F] frames of bpf bytes); when every tile starts on
-    // a 4-byte boundary the warp fetches the 32 tiles of its instances with coalesced word loads into shared
-    // memory and every lane then decodes its own instance from there, otherwise lanes read their bytes directly.
+    // a 4-byte boundary the warp fetches the 16 tiles of its instances with coalesced word loads into shared
+    // memory and every lane then decodes its own side from there, otherwise lanes read their bytes directly.
     const bool words_ok = ((reinterpret_cast<uintptr_t>(pcm) | ((size_t)F * bpf) | ((size_t)f_begin * bpf)) & 3u) == 0;
     const uint8_t *my_pcm = pcm + (size_t)inst * F * bpf;
-    const uint32_t n_inst = min(32u, d.N > inst0 ? d.N - inst0 : 0u);
+    const uint32_t n_inst = min(16u, d.N > inst16 ? d.N - inst16 : 0u);
     // asynchronous fetch of the tile starting at frame f0 into buffer `buf` (one commit group per call).  A last
     // word may run <= 2 bytes past a ragged tile: still inside the PCM buffer, because the very end of the
     // buffer is word-aligned (F * bpf is) and so is every tile start.
@@ -151,7 +149,7 @@ chain_pre_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_depth
         if (words_ok && f0 < f_end) {
             const uint32_t nwords = (min(32u, f_end - f0) * bpf + 3) / 4;
             for (uint32_t i = 0; i < n_inst; i++) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(pcm + ((size_t)(inst0 + i) * F + f0) * bpf);
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(pcm + ((size_t)(inst16 + i) * F + f0) * bpf);
                 for (uint32_t w = lane; w < nwords; w += 32) cp_async_4(&pcm_s[warp][buf][i][w], src + w);
             }
         }
@@ -167,66 +165,59 @@ chain_pre_kernel(ChainDev d, const uint8_t *__restrict__ pcm, uint32_t bit_depth
         if (words_ok) {
             cp_async_wait<1>();
             __syncwarp();
-            tile_bytes = reinterpret_cast<const uint8_t *>(pcm_s[warp][buf][lane]);
+            tile_bytes = reinterpret_cast<const uint8_t *>(pcm_s[warp][buf][li]);
         }
         for (uint32_t t = 0; t < nv; t++) {
             const uint8_t *q = tile_bytes + (size_t)t * bpf;
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                int32_t s = 0;
-                if (live) {
-                    if (bit_depth == 24) {
-                        const uint8_t *b = q + side * 3;
-                        s = ((int32_t)((uint32_t)b[2] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[0] << 8)) >> 8;
-                    } else {
-                        const uint8_t *b = q + side * 2;
-                        s = (int16_t)((uint16_t)b[0] | (uint16_t)b[1] << 8);
-                    }
+            int32_t sm = 0;
+            if (live) {
+                if (bit_depth == 24) {
+                    const uint8_t *b = q + side * 3;
+                    sm = ((int32_t)((uint32_t)b[2] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[0] << 8)) >> 8;
+                } else {
+                    const uint8_t *b = q + side * 2;
+                    sm = (int16_t)((uint16_t)b[0] | (uint16_t)b[1] << 8);
                 }
-                float v = __fmul_rn((float)s, gain_in[side]);                // :645-648 / :683-684
-                if (loud_on) {
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        if ((loud_byp >> j) & 1) continue;
-                        float &s0 = ls[side][j][0], &s1 = ls[side][j][1];
-                        const float v3 = __fadd_rn(v, -s1);
-                        const float pp = __fmul_rn(lc[j][1], v3);
-                        float t2, v1, v2;
-                        if (FUSED) {
-                            t2 = __fmaf_rn(lc[j][1], s0, s1);
-                            v1 = __fmaf_rn(lc[j][0], s0, pp);
-                            v2 = __fmaf_rn(lc[j][2], v3, t2);
-                        } else {
-                            t2 = __fadd_rn(s1, __fmul_rn(lc[j][1], s0));
-                            v1 = __fadd_rn(__fmul_rn(lc[j][0], s0), pp);
-                            v2 = __fadd_rn(t2, __fmul_rn(lc[j][2], v3));
-                        }
-                        s0 = __fmaf_rn(2.0f, v1, -s0);
-                        s1 = __fmaf_rn(2.0f, v2, -s1);
-                        v = fm<FUSED>(lc[j][5], v2, fm<FUSED>(lc[j][3], v, __fmul_rn(lc[j][4], v1)));   // :702
-                    }
-                }
-                tile[side][t][lane] = v;
             }
+            float v = __fmul_rn((float)sm, gain_in);                         // :645-648 / :683-684
+            if (loud_on) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    if ((loud_byp >> j) & 1) continue;
+                    float &s0 = ls[j][0], &s1 = ls[j][1];
+                    const float v3 = __fadd_rn(v, -s1);
+                    const float pp = __fmul_rn(lc[j][1], v3);
+                    float t2, v1, v2;
+                    if (FUSED) {
+                        t2 = __fmaf_rn(lc[j][1], s0, s1);
+                        v1 = __fmaf_rn(lc[j][0], s0, pp);
+                        v2 = __fmaf_rn(lc[j][2], v3, t2);
+                    } else {
+                        t2 = __fadd_rn(s1, __fmul_rn(lc[j][1], s0));
+                        v1 = __fadd_rn(__fmul_rn(lc[j][0], s0), pp);
+                        v2 = __fadd_rn(t2, __fmul_rn(lc[j][2], v3));
+                    }
+                    s0 = __fmaf_rn(2.0f, v1, -s0);
+                    s1 = __fmaf_rn(2.0f, v2, -s1);
+                    v = fm<FUSED>(lc[j][5], v2, fm<FUSED>(lc[j][3], v, __fmul_rn(lc[j][4], v1)));   // :702
+                }
+            }
+            tile[t][lane] = v;
         }
         __syncwarp();
         // transpose out: lane = frame, one coalesced 128-byte store per (side, instance) row
         if ((uint32_t)lane < nv) {
 #pragma unroll 8
-            for (int r = 0; r < 64; r++) {
-                const int side = r >> 5, i = r & 31;
-                d.mrow[((size_t)side * Np + inst0 + i) * d.ldF + f0 + lane] = tile[side][lane][i];
-            }
+            for (int r = 0; r < 32; r++)
+                d.mrow[((size_t)(r >> 4) * Np + inst16 + (r & 15)) * d.ldF + f0 + lane] = tile[lane][r];
         }
         __syncwarp();
     }
 #pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst] = ls[side][j][0];
-            d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst] = ls[side][j][1];
-        }
+    for (int j = 0; j < 2; j++) {
+        d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst] = ls[j][0];
+        d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst] = ls[j][1];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -816,6 +807,7 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
     }
     const ChainDev d = c->d;
     const uint32_t n_sms = st.rest_sms ? st.rest_sms : 148;     // SMs the streaming stages run on (chain_streams.cuh)
+    static const uint32_t kStreamCtas = [] { const char *e = getenv("DSPI_CHAIN_CTAS"); const int v = e ? atoi(e) : 0; return (uint32_t)(v >= 1 && v <= 8 ? v : 8); }();   // streaming CTAs (256 threads) per SM
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
     CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
@@ -823,7 +815,7 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
         const uint32_t fb = p0 * fpp, fe = p1 * fpp;
         int rc;
         // ---- front: unpack + loudness -> master EQ (K1) -> leveller + crossfeed
-        dspi::chain_pre_kernel<FUSED><<<(d.N_pad / 32 + 1) / 2, 64, 0, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, fb, fe, F);
+        dspi::chain_pre_kernel<FUSED><<<(d.N_pad / 16 + 1) / 2, 64, 0, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, fb, fe, F);
         CU_OK(cudaGetLastError());
         if ((rc = dspi::eq_process_on(c->eq_m, d.mrow + fb, fe - fb, d.ldF, st.s_front)) != DSPI_OK) return rc;
         post<<<(d.N_pad / 16 + 3) / 4, 128, post_smem, st.s_front>>>(d, p0, p1 - p0, fpp);
@@ -831,10 +823,10 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
         CU_OK(cudaEventRecord(st.ev_front[sl], st.s_front));
         // ---- outputs: matrix -> per-output EQ (K1) -> gain / delay / metering / conversion
         CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
-        dspi::chain_mix_kernel<FUSED><<<n_sms * 8, 256, 0, st.s_out>>>(d, fb, fe);
+        dspi::chain_mix_kernel<FUSED><<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, fb, fe);
         CU_OK(cudaGetLastError());
         if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
-        dspi::chain_outpost_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        dspi::chain_outpost_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
         // ---- modulator
@@ -843,7 +835,7 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
         CU_OK(cudaGetLastError());
         c->launches += 5;
     }
-    dspi::chain_ring_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, F, fpp);     // after the last outpost launch (stream order)
+    dspi::chain_ring_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, F, fpp);     // after the last outpost launch (stream order)
     CU_OK(cudaGetLastError());
     c->launches++;
     std::swap(c->d.widx_in, c->d.widx_out);

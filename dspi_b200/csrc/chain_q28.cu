@@ -99,40 +99,38 @@ __device__ __forceinline__ float gain_computer(float x_db, float threshold, floa
 __global__ void __launch_bounds__(64)
 chainq_pre_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_depth, uint32_t f_begin, uint32_t f_end, uint32_t F)
 {
-    __shared__ int32_t tile_s[2][2][32][kXs];
-    __shared__ uint32_t pcm_s[2][2][32][49];              // per warp, double-buffered: 32 instances x 32 frames x <= 6 bytes (rows padded to 49 words)
+    // warp = 16 instances x {L, R}, lane l = side l >> 4 of instance inst16 + (l & 15): see chain_pre_kernel (chain_f32.cu)
+    __shared__ int32_t tile_s[2][32][kXs];                // per warp: [frame][row = side * 16 + instance]
+    __shared__ uint32_t pcm_s[2][2][16][49];              // per warp, double-buffered: 16 instances x 32 frames x <= 6 bytes (rows padded to 49 words)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t inst0 = (blockIdx.x * 2 + warp) * 32;
-    if (inst0 >= d.N_pad) return;
-    const uint32_t inst = inst0 + lane;
+    const uint32_t inst16 = (blockIdx.x * 2 + warp) * 16;
+    if (inst16 >= d.N_pad) return;
+    const uint32_t side = lane >> 4, li = lane & 15;
+    const uint32_t inst = inst16 + li;
     const bool live = inst < d.N;
     const size_t Np = d.N_pad;
-    int32_t (*tile)[32][kXs] = tile_s[warp];
+    int32_t (*tile)[kXs] = tile_s[warp];
 
     const bool loud_on = d.flags[inst] & F_LOUD;
     const uint8_t loud_byp = d.loud_byp[inst];
-    int32_t lc[2][5], ls[2][2][2], preamp[2];
+    int32_t lc[2][5], ls[2][2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
 #pragma unroll
         for (int k = 0; k < 5; k++) lc[j][k] = d.loud_c[(j * 5 + k) * Np + inst];
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            ls[side][j][0] = d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst];
-            ls[side][j][1] = d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst];
-        }
+        ls[j][0] = d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst];
+        ls[j][1] = d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst];
     }
-    preamp[0] = d.preamp[inst];
-    preamp[1] = d.preamp[Np + inst];
+    const int32_t preamp = d.preamp[side * Np + inst];
     const uint32_t bpf = bit_depth == 24 ? 6u : 4u;
     const bool words_ok = ((reinterpret_cast<uintptr_t>(pcm) | ((size_t)F * bpf) | ((size_t)f_begin * bpf)) & 3u) == 0;
     const uint8_t *my_pcm = pcm + (size_t)inst * F * bpf;
-    const uint32_t n_inst = min(32u, d.N > inst0 ? d.N - inst0 : 0u);
+    const uint32_t n_inst = min(16u, d.N > inst16 ? d.N - inst16 : 0u);
     auto fetch = [&](uint32_t f0, int buf) {               // see chain_pre_kernel (chain_f32.cu)
         if (words_ok && f0 < f_end) {
             const uint32_t nwords = (min(32u, f_end - f0) * bpf + 3) / 4;
             for (uint32_t i = 0; i < n_inst; i++) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(pcm + ((size_t)(inst0 + i) * F + f0) * bpf);
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(pcm + ((size_t)(inst16 + i) * F + f0) * bpf);
                 for (uint32_t w = lane; w < nwords; w += 32) cp_async_4(&pcm_s[warp][buf][i][w], src + w);
             }
         }
@@ -148,53 +146,46 @@ chainq_pre_kernel(ChainQ d, const uint8_t *__restrict__ pcm, uint32_t bit_depth,
         if (words_ok) {
             cp_async_wait<1>();
             __syncwarp();
-            tile_bytes = reinterpret_cast<const uint8_t *>(pcm_s[warp][buf][lane]);
+            tile_bytes = reinterpret_cast<const uint8_t *>(pcm_s[warp][buf][li]);
         }
         for (uint32_t t = 0; t < nv; t++) {
             const uint8_t *q = tile_bytes + (size_t)t * bpf;
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                int32_t raw = 0;
-                if (live) {
-                    if (bit_depth == 24) {
-                        const uint8_t *b = q + side * 3;
-                        raw = ((int32_t)((uint32_t)b[2] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[0] << 8)) >> 2;       // :1001
-                    } else {
-                        const uint8_t *b = q + side * 2;
-                        raw = (int32_t)((uint32_t)(int32_t)(int16_t)((uint16_t)b[0] | (uint16_t)b[1] << 8) << 14);       // :1010
-                    }
+            int32_t raw = 0;
+            if (live) {
+                if (bit_depth == 24) {
+                    const uint8_t *b = q + side * 3;
+                    raw = ((int32_t)((uint32_t)b[2] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[0] << 8)) >> 2;       // :1001
+                } else {
+                    const uint8_t *b = q + side * 2;
+                    raw = (int32_t)((uint32_t)(int32_t)(int16_t)((uint16_t)b[0] | (uint16_t)b[1] << 8) << 14);       // :1010
                 }
-                int32_t x = mul_q28(raw, preamp[side]);
-                if (loud_on) {
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        if ((loud_byp >> j) & 1) continue;
-                        const int32_t result = mul_q28(lc[j][0], x) + ls[side][j][0];                                    // :1026
-                        ls[side][j][0] = mul_q28(lc[j][1], x) - mul_q28(lc[j][3], result) + ls[side][j][1];
-                        ls[side][j][1] = mul_q28(lc[j][2], x) - mul_q28(lc[j][4], result);
-                        x = result;
-                    }
-                }
-                tile[side][t][lane] = x;
             }
+            int32_t x = mul_q28(raw, preamp);
+            if (loud_on) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    if ((loud_byp >> j) & 1) continue;
+                    const int32_t result = mul_q28(lc[j][0], x) + ls[j][0];                                          // :1026
+                    ls[j][0] = mul_q28(lc[j][1], x) - mul_q28(lc[j][3], result) + ls[j][1];
+                    ls[j][1] = mul_q28(lc[j][2], x) - mul_q28(lc[j][4], result);
+                    x = result;
+                }
+            }
+            tile[t][lane] = x;
         }
         __syncwarp();
         if ((uint32_t)lane < nv) {
 #pragma unroll 8
-            for (int r = 0; r < 64; r++) {
-                const int side = r >> 5, i = r & 31;
-                d.mrow[((size_t)side * Np + inst0 + i) * d.ldF + f0 + lane] = tile[side][lane][i];
-            }
+            for (int r = 0; r < 32; r++)
+                d.mrow[((size_t)(r >> 4) * Np + inst16 + (r & 15)) * d.ldF + f0 + lane] = tile[lane][r];
         }
         __syncwarp();
     }
 #pragma unroll
-    for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst] = ls[side][j][0];
-            d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst] = ls[side][j][1];
-        }
+    for (int j = 0; j < 2; j++) {
+        d.loud_st[((side * 2 + j) * 2 + 0) * Np + inst] = ls[j][0];
+        d.loud_st[((side * 2 + j) * 2 + 1) * Np + inst] = ls[j][1];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1146,23 +1137,24 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
     }
     const ChainQ d = c->d;
     const uint32_t n_sms = st.rest_sms ? st.rest_sms : 148;     // SMs the streaming stages run on (chain_streams.cuh)
+    static const uint32_t kStreamCtas = [] { const char *e = getenv("DSPI_CHAIN_CTAS"); const int v = e ? atoi(e) : 0; return (uint32_t)(v >= 1 && v <= 8 ? v : 8); }();   // streaming CTAs (256 threads) per SM
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
     CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t p0 = slice_bounds[sl], p1 = slice_bounds[sl + 1];
         const uint32_t fb = p0 * fpp, fe = p1 * fpp;
         int rc;
-        dspi::chainq_pre_kernel<<<(d.N_pad / 32 + 1) / 2, 64, 0, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, fb, fe, F);
+        dspi::chainq_pre_kernel<<<(d.N_pad / 16 + 1) / 2, 64, 0, st.s_front>>>(d, (const uint8_t *)d_pcm, bit_depth, fb, fe, F);
         CU_OK(cudaGetLastError());
         if ((rc = dspi::eq_process_on(c->eq_m, d.mrow + fb, fe - fb, d.ldF, st.s_front)) != DSPI_OK) return rc;
         dspi::chainq_post_kernel<<<(d.N_pad / 16 + 3) / 4, 128, post_smem, st.s_front>>>(d, p0, p1 - p0, fpp);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_front[sl], st.s_front));
         CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
-        dspi::chainq_mix_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, fb, fe);
+        dspi::chainq_mix_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, fb, fe);
         CU_OK(cudaGetLastError());
         if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
-        dspi::chainq_outpost_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        dspi::chainq_outpost_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
         CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
@@ -1170,7 +1162,7 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
         CU_OK(cudaGetLastError());
         c->launches += 5;
     }
-    dspi::chainq_ring_kernel<<<n_sms * 8, 256, 0, st.s_out>>>(d, F, fpp);            // after the last outpost launch (stream order)
+    dspi::chainq_ring_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, F, fpp);            // after the last outpost launch (stream order)
     CU_OK(cudaGetLastError());
     c->launches++;
     std::swap(c->d.widx_in, c->d.widx_out);

@@ -9,13 +9,14 @@
 // 10 bands pre-split into (c>>16, c&0xFFFF, (c>>16)<<4) and held in registers together with
 // s1/s2; samples stream through the same per-warp TMA ring as the float kernel (eq_f32.cu).
 // Per multiply: 3 IMAD + 1 SHF; the path is bound by the integer pipes, not by HBM.
+#include <cstdlib>
 #include "eq_kernels.cuh"
 
 namespace dspi {
 namespace {
 
 constexpr int kTileT = 32;
-constexpr int kSub = 8;
+constexpr int kSubMax = 8;     // samples per register tile: 8 (round 1) or 4 (half the straight-line code; see launch_one)
 constexpr int kStages = 3;
 constexpr int kWarps = 8;
 constexpr int kRows = 32;
@@ -71,7 +72,7 @@ __device__ __noinline__ uint2 q28_slow_band(uint32_t *xs, int n, const int32_t *
     return make_uint2(s1, s2);
 }
 
-template <int NB>
+template <int NB, int kSub>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ samples, uint32_t ld, int32_t *__restrict__ coef,
               uint32_t n_groups, uint32_t n_rows, uint32_t T, uint32_t nb_active, uint32_t use_tma)
@@ -148,9 +149,12 @@ eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ sa
             const int nvalid = min(kSub, tile_valid - sub * kSub);
             if (nvalid <= 0) break;
             uint8_t *row = buf + lane * 128;
-            const uint4 q0 = *reinterpret_cast<const uint4 *>(row + (((2 * sub) << 4) ^ sw));
-            const uint4 q1 = *reinterpret_cast<const uint4 *>(row + (((2 * sub + 1) << 4) ^ sw));
-            uint32_t x[kSub] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+            uint32_t x[kSub];
+#pragma unroll
+            for (int c = 0; c < kSub / 4; c++) {                              // 16-byte chunks of this lane's row, chunk index XOR (row & 7)
+                const uint4 q = *reinterpret_cast<const uint4 *>(row + ((((kSub / 4) * sub + c) << 4) ^ sw));
+                x[4 * c] = q.x; x[4 * c + 1] = q.y; x[4 * c + 2] = q.z; x[4 * c + 3] = q.w;
+            }
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 if (b >= (int)nb_active) break;
@@ -183,8 +187,9 @@ eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ sa
                     for (int i = 0; i < kSub; i++) x[i] = xs[i];
                 }
             }
-            *reinterpret_cast<uint4 *>(row + (((2 * sub) << 4) ^ sw)) = make_uint4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<uint4 *>(row + (((2 * sub + 1) << 4) ^ sw)) = make_uint4(x[4], x[5], x[6], x[7]);
+#pragma unroll
+            for (int c = 0; c < kSub / 4; c++)
+                *reinterpret_cast<uint4 *>(row + ((((kSub / 4) * sub + c) << 4) ^ sw)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
         }
         if (use_tma) {
             fence_proxy_async_smem();
@@ -217,11 +222,11 @@ eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ sa
     if (use_tma && lane == 0) tma_store_wait_all<0>();
 }
 
-template <int NB>
+template <int NB, int SUB>
 cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
 {
     constexpr size_t smem = (size_t)kWarps * kStages * kStageBytes;
-    auto kern = eq_q28_kernel<NB>;
+    auto kern = eq_q28_kernel<NB, SUB>;
     static PerDeviceOnce once;
     int dev = 0;
     if (once.needs(&dev)) {
@@ -238,8 +243,12 @@ cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
 
 cudaError_t launch_eq_q28(const EqLaunch &a, cudaStream_t stream)
 {
-    if (a.n_bands <= 10) return launch_one<10>(a, stream);
-    return launch_one<12>(a, stream);
+    // register tile of 8 or 4 samples (DSPI_K2_SUB): the straight-line body is 10 bands x tile x ~27 instructions, 35 KB at 8.
+    // Halving it to cure the instruction-fetch stalls ncu shows costs more than it saves: 32768 ch x 6144 on B200 run at
+    // 63.9 G samples/s with 8-sample tiles and 56.2 G with 4 (less independent work between dependent IMADs), so 8 stays.
+    static const int sub = [] { const char *e = getenv("DSPI_K2_SUB"); return (e && atoi(e) == 8) ? 8 : ((e && atoi(e) == 4) ? 4 : 8); }();
+    if (a.n_bands <= 10) return sub == 4 ? launch_one<10, 4>(a, stream) : launch_one<10, 8>(a, stream);
+    return sub == 4 ? launch_one<12, 4>(a, stream) : launch_one<12, 8>(a, stream);
 }
 
 __global__ void pack_q28_kernel(const dspi_biquad_q28 *__restrict__ aos, uint32_t ch0, uint32_t n, int32_t *__restrict__ coef)

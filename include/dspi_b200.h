@@ -522,7 +522,10 @@ uint32_t dspi_crc32(const void *data, size_t len);               /* flash_storag
  * (MASTER_VOLUME_MODE_INDEPENDENT = 0: use dir_master_volume_db; 1: the slot's own value when version >= 12). */
 int dspi_preset_slot_apply(const void *slot, size_t len, uint8_t slot_index, uint8_t master_volume_mode, float dir_master_volume_db,
                            dspi_bulk_state *st);
-/* collect_live_state() (:464-556): writes dspi_preset_slot_size(st->platform) bytes (pins, names, I2S: zero) */
+/* collect_live_state() (:464-556): writes dspi_preset_slot_size(st->platform) bytes with a valid header and CRC.
+ * dspi_bulk_state carries the DSP state only: output pins, channel names, output types and the I2S fields are written as
+ * ZERO, so the image is for exchanging DSP state between hosts of this library (apply ignores those fields) - do NOT
+ * flash it onto a device, which would load the zeros over its pin / name / I2S configuration. */
 int dspi_preset_slot_collect(const dspi_bulk_state *st, uint8_t slot_index, void *out, size_t cap);
 
 /* ---- S/PDIF (IEC 60958) subframe encoder: the step after the chain -------------------------- */
