@@ -536,6 +536,16 @@ int eq_process_on(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStre
     return launch_eq(e, d_samples, T, ld, 0, e->n_groups, e->desc.n_channels, s);
 }
 
+// channels [ch0, ch0 + n) on a stream of the caller's choosing (launches over disjoint channel ranges may run concurrently:
+// they touch disjoint parts of the coefficient / state store)
+int eq_process_range_on(dspi_eq *e, void *d_rows, uint32_t T, uint32_t ld, uint32_t ch0, uint32_t n, cudaStream_t s)
+{
+    if (T == 0 || n == 0) return DSPI_OK;
+    if (ch0 % e->rows) return fail(DSPI_EINVAL, "first channel %u is not a multiple of the engine's group size %u", ch0, e->rows);
+    CU_OK(cudaSetDevice(e->desc.device));
+    return launch_eq(e, d_rows, T, ld, ch0 / e->rows, (n + e->rows - 1) / e->rows, n, s);
+}
+
 }  // namespace dspi
 
 extern "C" {

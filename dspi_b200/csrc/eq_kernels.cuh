@@ -66,6 +66,7 @@ int eq_unpack_range(dspi_eq *e, uint32_t ch0, uint32_t n, cudaStream_t s); // pa
 // device memory owned by the caller; call again after changing it.
 int eq_set_skip(dspi_eq *e, const uint8_t *d_skip, cudaStream_t s);
 int eq_process_on(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld, cudaStream_t s);
+int eq_process_range_on(dspi_eq *e, void *d_rows, uint32_t T, uint32_t ld, uint32_t ch0, uint32_t n, cudaStream_t s);
 // staged copy-in / kernel / copy-out pipeline of channels [ch0, ch0 + n_ch) against `remote` rows [n_ch][T] (pinned host
 // memory or a peer GPU's memory); enqueue does not block, wait returns when the results are back in `remote`
 int eq_process_remote_enqueue(dspi_eq *e, void *remote, uint32_t T, uint32_t ch0, uint32_t n_ch);

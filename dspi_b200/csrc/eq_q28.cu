@@ -16,7 +16,6 @@ namespace dspi {
 namespace {
 
 constexpr int kTileT = 32;
-constexpr int kSubMax = 8;     // samples per register tile: 8 (round 1) or 4 (half the straight-line code; see launch_one)
 constexpr int kStages = 3;
 constexpr int kWarps = 8;
 constexpr int kRows = 32;
@@ -151,9 +150,9 @@ eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ sa
             uint8_t *row = buf + lane * 128;
             uint32_t x[kSub];
 #pragma unroll
-            for (int c = 0; c < kSub / 4; c++) {                              // 16-byte chunks of this lane's row, chunk index XOR (row & 7)
-                const uint4 q = *reinterpret_cast<const uint4 *>(row + ((((kSub / 4) * sub + c) << 4) ^ sw));
-                x[4 * c] = q.x; x[4 * c + 1] = q.y; x[4 * c + 2] = q.z; x[4 * c + 3] = q.w;
+            for (int h = 0; h < kSub / 4; h++) {                              // 16-byte chunks of this lane's row, chunk index XOR (row & 7)
+                const uint4 q = *reinterpret_cast<const uint4 *>(row + ((((kSub / 4) * sub + h) << 4) ^ sw));
+                x[4 * h] = q.x; x[4 * h + 1] = q.y; x[4 * h + 2] = q.z; x[4 * h + 3] = q.w;
             }
 #pragma unroll
             for (int b = 0; b < NB; b++) {
@@ -188,8 +187,8 @@ eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ sa
                 }
             }
 #pragma unroll
-            for (int c = 0; c < kSub / 4; c++)
-                *reinterpret_cast<uint4 *>(row + ((((kSub / 4) * sub + c) << 4) ^ sw)) = make_uint4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            for (int h = 0; h < kSub / 4; h++)
+                *reinterpret_cast<uint4 *>(row + ((((kSub / 4) * sub + h) << 4) ^ sw)) = make_uint4(x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3]);
         }
         if (use_tma) {
             fence_proxy_async_smem();

@@ -6,12 +6,15 @@
 // transfer of chunk j+1 overlaps the kernel of chunk j.  One process per GPU (torchrun); the communicator is created here
 // from a unique id the caller distributes (dspi_b200/sharding.py broadcasts it over torch.distributed).
 //
-// Pipeline, step j = 0 .. K+1, all enqueued from the host without waiting (events order the three streams):
-//     comm stream   one NCCL group:  root  -> every peer  chunk j      (ncclSend / ncclRecv)
-//                                    peers -> root        chunk j-2    (both NVLink directions busy in the same kernel)
-//     engine stream K1 / K2 over chunk j-1 of the rank's shard (dspi_eq_process_device_range's launch)
-// A peer keeps a ring of THREE chunk buffers (receiving, computing, sending); the root works in place on the caller's
-// block.  Chunks are row ranges on 64-channel boundaries; sharding and chunking change no bit.
+// Pipeline, step j = 0 .. K+L-1, all enqueued from the host without waiting (events order the streams):
+//     comm stream     one NCCL group:  root  -> every peer  chunk j      (ncclSend / ncclRecv)
+//                                      peers -> root        chunk j-L    (both NVLink directions busy in the same kernel)
+//     compute streams K1 / K2 over the chunks that have arrived, chunk j on stream j mod S
+// A cascade kernel runs as long as its rows are long however few rows it gets (parallel over channels, serial over time:
+// ~1 ms for 6144 frames) but a chunk of a shard fills only a few SMs, so the kernels of consecutive chunks run CONCURRENTLY
+// on several streams and a chunk travels back L steps after it arrived (L = kernel time / step time, rounded up, + 1).
+// A peer keeps a ring of L + 2 chunk buffers; the root works in place on the caller's block.  Chunks are row ranges on
+// 64-channel boundaries; sharding, chunking and the concurrency change no bit.
 //
 // libnccl is dlopen'ed (the copy torch already loaded when there is one), so the library has no link-time dependency on it
 // and single-GPU users never touch it.
@@ -68,7 +71,7 @@ const Nccl &nccl()
     return n;
 }
 
-constexpr int kRing = 3;
+constexpr int kMaxLag = 30, kMaxRing = kMaxLag + 2, kStreams = 8;
 
 }  // namespace
 
@@ -77,8 +80,10 @@ struct dspi_sg {
     int rank, world, root, device;
     ncclComm_t comm;
     cudaStream_t s_comm;
+    cudaStream_t s_comp[kStreams];
     std::vector<cudaEvent_t> ev_recv, ev_done;     // per chunk
-    void *ring[kRing];
+    void *ring[kMaxRing];
+    int ring_slots;
     size_t ring_bytes;
     uint32_t rows;                                  // channels of this rank's shard == engine channels
 };
@@ -114,9 +119,10 @@ int dspi_sg_destroy(dspi_sg *g)
     if (g->s_comm) cudaStreamSynchronize(g->s_comm);
     for (cudaEvent_t e : g->ev_recv) cudaEventDestroy(e);
     for (cudaEvent_t e : g->ev_done) cudaEventDestroy(e);
-    for (int i = 0; i < kRing; i++) if (g->ring[i]) cudaFree(g->ring[i]);
+    for (int i = 0; i < kMaxRing; i++) if (g->ring[i]) cudaFree(g->ring[i]);
     if (g->comm) nccl().CommDestroy(g->comm);
     if (g->s_comm) cudaStreamDestroy(g->s_comm);
+    for (int i = 0; i < kStreams; i++) if (g->s_comp[i]) { cudaStreamSynchronize(g->s_comp[i]); cudaStreamDestroy(g->s_comp[i]); }
     delete g;
     cudaGetLastError();
     return DSPI_OK;
@@ -131,10 +137,12 @@ int dspi_sg_create(dspi_sg **out, dspi_eq *engine, int device, const void *id128
     dspi_sg *g = new (std::nothrow) dspi_sg();
     if (!g) return failn(DSPI_ENOMEM, "host allocation failed");
     g->eng = engine; g->rank = rank; g->world = world; g->root = root; g->device = device;
-    g->comm = nullptr; g->s_comm = nullptr; g->ring_bytes = 0; g->rows = 0;
-    for (int i = 0; i < kRing; i++) g->ring[i] = nullptr;
+    g->comm = nullptr; g->s_comm = nullptr; g->ring_bytes = 0; g->ring_slots = 0; g->rows = 0;
+    for (int i = 0; i < kMaxRing; i++) g->ring[i] = nullptr;
+    for (int i = 0; i < kStreams; i++) g->s_comp[i] = nullptr;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->s_comm, cudaStreamNonBlocking);
+    for (int i = 0; i < kStreams && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&g->s_comp[i], cudaStreamNonBlocking);
     if (e != cudaSuccess) { dspi_sg_destroy(g); return failn(DSPI_ECUDA, "stream: %s", cudaGetErrorString(e)); }
     ncclUniqueId id;
     memcpy(&id, id128, 128);
@@ -158,16 +166,13 @@ int dspi_sg_process(dspi_sg *g, void *d_full, uint32_t total_channels, uint32_t 
     const int W = g->world;
     std::vector<uint32_t> lo(W), hi(W);
     for (int r = 0; r < W; r++) dspi_eqx_shard_range(total_channels, (uint32_t)W, (uint32_t)r, &lo[r], &hi[r]);
-    if (n_chunks == 0) {
-        // Automatic chunk count.  A cascade kernel runs as long as its rows are long, however few rows it is given
-        // (parallel over channels, serial over time: ~0.17 us per frame, one wave for <= 65536 channels), so a pipeline
-        // step costs max(transfer of one chunk, one kernel): more chunks only help while a chunk's transfer still takes
-        // longer than a kernel.  Transfer time of one direction: the root moves every peer's shard over its own links
-        // (measured 575 - 710 GB/s with grouped ncclSend / ncclRecv, profiles/r2_nccl_sg_*.txt).
-        const double t_dir = (double)(total_channels - (hi[g->root] - lo[g->root])) * T * 4.0 / 650e9;
-        const double t_kernel = (double)T * 0.17e-6;
-        double k = t_dir / t_kernel;
-        n_chunks = k < 2.0 ? 2u : (k > 16.0 ? 16u : (uint32_t)k);
+    // Transfer time of one direction: the root moves every peer's shard over its own links (measured 575 - 710 GB/s with
+    // grouped ncclSend / ncclRecv, profiles/r2_nccl_sg_*.txt); kernel time: ~0.17 us per frame (float; the Q28 cascade ~6x).
+    const double t_dir = (double)(total_channels - (hi[g->root] - lo[g->root])) * T * 4.0 / 650e9;
+    const double t_kernel = (double)T * 0.17e-6 * 1.1;
+    if (n_chunks == 0) {                                                     // automatic: steps of about half a millisecond
+        const double k = t_dir / 0.5e-3;
+        n_chunks = k < 4.0 ? 4u : (k > 32.0 ? 32u : (uint32_t)k);
     }
     const uint32_t my_rows = hi[g->rank] - lo[g->rank];
     // chunk ranges of a shard: <= n_chunks pieces on 64-row boundaries; identical arithmetic on every rank
@@ -185,14 +190,20 @@ int dspi_sg_process(dspi_sg *g, void *d_full, uint32_t total_channels, uint32_t 
         }
     }
     const uint32_t my_per = chunk_rows(my_rows), my_k = my_rows ? n_of(my_rows) : 0;
+    // lag between a chunk's arrival and its return: its kernel must have finished, and kernels of consecutive chunks overlap
+    uint32_t L = (uint32_t)(t_kernel / (t_dir / (double)K)) + 2u;
+    if (L < 2u) L = 2u;
+    if (L > (uint32_t)kMaxLag) L = (uint32_t)kMaxLag;
+    const uint32_t R = L + 2u;                                               // ring slots of a peer
     if (!is_root) {
         const size_t need = (size_t)my_per * T * 4;
-        if (need > g->ring_bytes) {
+        if (need > g->ring_bytes || (int)R > g->ring_slots) {
             CU_OKN(cudaStreamSynchronize(g->s_comm));
-            for (int i = 0; i < kRing; i++) { if (g->ring[i]) cudaFree(g->ring[i]); g->ring[i] = nullptr; }
-            g->ring_bytes = 0;
-            for (int i = 0; i < kRing; i++) CU_OKN(cudaMalloc(&g->ring[i], need));
-            g->ring_bytes = need;
+            for (int i = 0; i < kStreams; i++) CU_OKN(cudaStreamSynchronize(g->s_comp[i]));
+            for (int i = 0; i < kMaxRing; i++) { if (g->ring[i]) cudaFree(g->ring[i]); g->ring[i] = nullptr; }
+            g->ring_bytes = 0; g->ring_slots = 0;
+            for (uint32_t i = 0; i < R; i++) CU_OKN(cudaMalloc(&g->ring[i], need));
+            g->ring_bytes = need; g->ring_slots = (int)R;
         }
     }
     // the root's own rows need no transfer: its kernel runs beside the transfers, in place
@@ -201,9 +212,8 @@ int dspi_sg_process(dspi_sg *g, void *d_full, uint32_t total_channels, uint32_t 
         if (rc) return rc;
     }
     if (W == 1) { CU_OKN(cudaStreamSynchronize(s_eng)); return DSPI_OK; }
-    for (uint32_t j = 0; j < K + 2; j++) {
-        if (!is_root && j >= 2 && j - 2 < my_k) CU_OKN(cudaStreamWaitEvent(g->s_comm, g->ev_done[j - 2], 0));     // results of chunk j-2 are complete
-        if (!is_root && j >= (uint32_t)kRing && j < my_k) CU_OKN(cudaStreamWaitEvent(g->s_comm, g->ev_done[j - kRing], 0));   // ring slot reused (implied by the send, kept explicit)
+    for (uint32_t j = 0; j < K + L; j++) {
+        if (!is_root && j >= L && j - L < my_k) CU_OKN(cudaStreamWaitEvent(g->s_comm, g->ev_done[j - L], 0));      // results of chunk j-L are complete
         NC_OK(nccl().GroupStart());
         if (is_root) {
             for (int r = 0; r < W; r++) {
@@ -213,31 +223,33 @@ int dspi_sg_process(dspi_sg *g, void *d_full, uint32_t total_channels, uint32_t 
                     const uint32_t a = j * per, b = (a + per < rows) ? a + per : rows;
                     NC_OK(nccl().Send((char *)d_full + ((size_t)lo[r] + a) * T * 4, (size_t)(b - a) * T, ncclFloat, r, g->comm, g->s_comm));
                 }
-                if (j >= 2 && j - 2 < k) {
-                    const uint32_t a = (j - 2) * per, b = (a + per < rows) ? a + per : rows;
+                if (j >= L && j - L < k) {
+                    const uint32_t a = (j - L) * per, b = (a + per < rows) ? a + per : rows;
                     NC_OK(nccl().Recv((char *)d_full + ((size_t)lo[r] + a) * T * 4, (size_t)(b - a) * T, ncclFloat, r, g->comm, g->s_comm));
                 }
             }
         } else {
-            if (j < my_k) {
+            if (j < my_k) {                                                  // slot j mod R was last sent from at step j - R + L < j: free
                 const uint32_t a = j * my_per, b = (a + my_per < my_rows) ? a + my_per : my_rows;
-                NC_OK(nccl().Recv(g->ring[j % kRing], (size_t)(b - a) * T, ncclFloat, g->root, g->comm, g->s_comm));
+                NC_OK(nccl().Recv(g->ring[j % R], (size_t)(b - a) * T, ncclFloat, g->root, g->comm, g->s_comm));
             }
-            if (j >= 2 && j - 2 < my_k) {
-                const uint32_t a = (j - 2) * my_per, b = (a + my_per < my_rows) ? a + my_per : my_rows;
-                NC_OK(nccl().Send(g->ring[(j - 2) % kRing], (size_t)(b - a) * T, ncclFloat, g->root, g->comm, g->s_comm));
+            if (j >= L && j - L < my_k) {
+                const uint32_t a = (j - L) * my_per, b = (a + my_per < my_rows) ? a + my_per : my_rows;
+                NC_OK(nccl().Send(g->ring[(j - L) % R], (size_t)(b - a) * T, ncclFloat, g->root, g->comm, g->s_comm));
             }
         }
         NC_OK(nccl().GroupEnd());
-        if (!is_root && j < my_k) {                                          // chunk j arrived: its kernel overlaps the next step's transfers
+        if (!is_root && j < my_k) {                                          // chunk j arrived: its kernel starts on its own stream
+            cudaStream_t cs = g->s_comp[j % kStreams];
             CU_OKN(cudaEventRecord(g->ev_recv[j], g->s_comm));
-            CU_OKN(cudaStreamWaitEvent(s_eng, g->ev_recv[j], 0));
+            CU_OKN(cudaStreamWaitEvent(cs, g->ev_recv[j], 0));
             const uint32_t a = j * my_per, b = (a + my_per < my_rows) ? a + my_per : my_rows;
-            const int rc = dspi_eq_process_device_range(g->eng, g->ring[j % kRing], T, T, a, b - a);
+            const int rc = dspi::eq_process_range_on(g->eng, g->ring[j % R], T, T, a, b - a, cs);
             if (rc) return rc;
-            CU_OKN(cudaEventRecord(g->ev_done[j], s_eng));
+            CU_OKN(cudaEventRecord(g->ev_done[j], cs));
         }
     }
+    for (int i = 0; i < kStreams; i++) CU_OKN(cudaStreamSynchronize(g->s_comp[i]));
     CU_OKN(cudaStreamSynchronize(g->s_comm));
     CU_OKN(cudaStreamSynchronize(s_eng));
     return DSPI_OK;

@@ -67,10 +67,13 @@ def native(k):
 
 res = {"world": world, "bytes_each_way": (total - Cn) * T * 4}
 res["plain_ms"] = timeit(plain) * 1e3
-for k in (2, 4):
-    res[f"piped_{k}_ms"] = timeit(lambda: piped(k)) * 1e3
-for k in (1, 4, 8, 16, 32):
+ks = [int(v) for v in os.environ.get("SG_CHUNKS", "1,2,4,8,16").split(",")]
+if os.environ.get("SG_TORCH", "1") == "1":
+    for k in (2, 4):
+        res[f"piped_{k}_ms"] = timeit(lambda: piped(k)) * 1e3
+for k in ks:
     res[f"native_{k}_ms"] = timeit(lambda: native(k)) * 1e3
+res["native_auto_ms"] = timeit(lambda: native(0)) * 1e3
 if rank == 0:
     for k, v in list(res.items()):
         if k.endswith("_ms"):

@@ -389,3 +389,32 @@ def test_gpu_chain_against_the_committed_reference_vectors(flavour):
         assert [int(s["clip_flags"]) for s in status] == [int(c) for c in g[f"{flavour}_clip"]]
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("flavour", ["f32f", "q28"])
+def test_sm_partition_and_slice_plan_change_no_bit(oracle, flavour, monkeypatch):
+    """The modulator's SM partition (CUDA green contexts) and the slice plan are scheduling only: the same call with the
+    partition off / eight equal slices returns the same bytes, and the engine reports the split it runs under."""
+    N, n_packets, fpp = 200, 24, 96
+    P, bq = _params(oracle, flavour, N, 950)
+    pcm = pcm_bytes(N, n_packets * fpp, 24, 951)
+    outs = []
+    for env in ({}, {"DSPI_PDM_SMS": "0"}, {"DSPI_UNIFORM_SLICES": "1"}, {"DSPI_PDM_SMS": "16", "DSPI_UNIFORM_SLICES": "12"}):
+        for k in ("DSPI_PDM_SMS", "DSPI_UNIFORM_SLICES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = _engine(flavour, N, n_packets * fpp)
+        try:
+            part = eng.sm_partition()
+            if env.get("DSPI_PDM_SMS") == "0":
+                assert part == (0, 0)
+            elif "DSPI_PDM_SMS" not in env:
+                assert part == (0, 0) or (part[0] == 8 and part[1] > 0)      # 200 instances: 2 modulator CTAs -> the 8-SM minimum
+            eng.set_params(P)
+            eng.upload_biquads(bq)
+            outs.append(eng.process_host(pcm, 24, n_packets, fpp))
+        finally:
+            eng.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and o[2].tobytes() == outs[0][2].tobytes()
