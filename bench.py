@@ -421,7 +421,7 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         nccl = {"value": float(total) * T * n_sg / float(dt.item()), "unit": "samples/s", "steps": n_sg,
-                "path": "rank 0 holds all frames: dspi_sg_process - row chunks (count chosen from transfer / kernel time), one NCCL group per step carries chunk j out and chunk j-2 back while the kernels work on chunk j-1",
+                "path": "rank 0 holds all frames: dspi_sg_process - row chunks (count chosen from transfer / kernel time), one NCCL group per step carries chunk j out and chunk j-L back while the kernels work on the chunks in between, each on its own stream (L from kernel / step time)",
                 "bytes_over_nvlink_per_step": int(total - Cn) * T * 4 * 2}
         del full
         sg.close()

@@ -194,10 +194,12 @@ uint64_t dspi_eqx_launch_count(dspi_eqx *x);
 /* ---- one rank per GPU: frames that originate on one rank, over NCCL ------------------------- */
 /* Multi-PROCESS form of dspi_eqx_process_root: every rank owns an EQ engine over its shard
  * [lo_r, hi_r) = dspi_eqx_shard_range(total, world, r); the block [total][T] lives on the root rank.  dspi_sg_process
- * scatters it in row chunks with grouped ncclSend / ncclRecv, runs the engines on chunk j-1 while chunk j travels out and
- * chunk j-2 travels back in the same NCCL group (both NVLink directions busy), and leaves the results in the root's block.
- * n_chunks = 0 lets the library choose (a cascade kernel takes as long as its rows are long however few rows it gets, so
- * more chunks only pay while one chunk's transfer still outlasts a kernel).  libnccl.so.2 is dlopen'ed at first use.  The 128-byte unique id comes from dspi_nccl_unique_id() on one rank and is
+ * scatters it in row chunks with grouped ncclSend / ncclRecv: step j carries chunk j out and chunk j-L back in the same
+ * NCCL group (both NVLink directions busy) while the engines work on the chunks in between, each chunk's kernel on a
+ * stream of its own (a cascade kernel takes as long as its rows are long however few rows it gets, but a chunk fills only
+ * a few SMs); the results end up in the root's block.  n_chunks = 0 lets the library choose chunk count and lag from the
+ * transfer / kernel time ratio.  libnccl.so.2 is dlopen'ed at first use.  The 128-byte unique id comes from
+ * dspi_nccl_unique_id() on one rank and is
  * handed to the others by the caller (dspi_b200/sharding.py broadcasts it with torch.distributed). */
 typedef struct dspi_sg dspi_sg;
 int dspi_nccl_unique_id(void *id128);
