@@ -74,7 +74,7 @@ __device__ __noinline__ uint2 q28_slow_band(uint32_t *xs, int n, const int32_t *
 template <int NB, int kSub>
 __global__ void __launch_bounds__(kWarps * 32, 1)
 eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ samples, uint32_t ld, int32_t *__restrict__ coef,
-              uint32_t n_groups, uint32_t n_rows, uint32_t T, uint32_t nb_active, uint32_t use_tma)
+              uint32_t n_groups, uint32_t n_rows, uint32_t T, uint32_t nb_active, uint32_t use_tma, uint32_t no_plain)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bars[kWarps][kStages];
@@ -127,6 +127,7 @@ eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ sa
     }
 
     const uint32_t sw = (lane & 7) << 4;
+    const bool straight = nb_active >= (uint32_t)NB && all_byp == 0 && !no_plain;
     for (uint32_t tile = 0; tile < ntiles; tile++) {
         const uint32_t s = tile % kStages;
         uint8_t *buf = my_smem + s * kStageBytes;
@@ -154,6 +155,30 @@ eq_q28_kernel(const __grid_constant__ CUtensorMap tmap, int32_t *__restrict__ sa
                 const uint4 q = *reinterpret_cast<const uint4 *>(row + ((((kSub / 4) * sub + h) << 4) ^ sw));
                 x[4 * h] = q.x; x[4 * h + 1] = q.y; x[4 * h + 2] = q.z; x[4 * h + 3] = q.w;
             }
+            // Warps in which no band can be skipped outright get ONE straight-line block over all bands, so that ptxas overlaps
+            // band b+1's first samples with band b's last ones (the per-band branches below fence the scheduler: 32768 ch x 6144 on
+            // B200 ran at 62 G samples/s through them and run at 90 G through this block).  Lanes with a bypassed band keep their
+            // input and state through selects instead of a branch.
+            if (straight && nvalid == kSub) {
+                if (any_byp == 0) {
+#pragma unroll
+                    for (int b = 0; b < NB; b++) q28_tile(x, c[b], s1[b], s2[b]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < NB; b++) {
+                        uint32_t keep[kSub];
+#pragma unroll
+                        for (int i = 0; i < kSub; i++) keep[i] = x[i];
+                        const uint32_t k1 = s1[b], k2 = s2[b];
+                        q28_tile(x, c[b], s1[b], s2[b]);
+                        const bool off = (byp >> b) & 1u;
+#pragma unroll
+                        for (int i = 0; i < kSub; i++) x[i] = off ? keep[i] : x[i];
+                        s1[b] = off ? k1 : s1[b];
+                        s2[b] = off ? k2 : s2[b];
+                    }
+                }
+            } else
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 if (b >= (int)nb_active) break;
@@ -234,7 +259,8 @@ cudaError_t launch_one(const EqLaunch &a, cudaStream_t stream)
         once.mark(dev);
     }
     const uint32_t grid = (a.n_groups + kWarps - 1) / kWarps;
-    kern<<<grid, kWarps * 32, smem, stream>>>(a.tmap, (int32_t *)a.samples, a.ld, (int32_t *)a.coef, a.n_groups, a.n_rows, a.T, a.n_bands, a.use_tma);
+    static const uint32_t no_plain = [] { const char *e = getenv("DSPI_K2_PLAIN"); return (e && atoi(e) == 0) ? 1u : 0u; }();
+    kern<<<grid, kWarps * 32, smem, stream>>>(a.tmap, (int32_t *)a.samples, a.ld, (int32_t *)a.coef, a.n_groups, a.n_rows, a.T, a.n_bands, a.use_tma, no_plain);
     return cudaGetLastError();
 }
 
