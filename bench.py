@@ -360,7 +360,8 @@ def main():
                 "peak_source": peak_src, "kernel": "eq_q28_kernel" if q else ("eq_f32_jit" if kernel_info.startswith("jit") else "eq_f32_kernel"),
                 "kernel_variant": kernel_info,
                 "algorithmic_bytes_per_launch": Cn * T * ALG_BYTES_PER_SAMPLE,
-                "note": "FP32-issue bound, not HBM bound: see DESIGN.md (60 FMA-pipe lane-ops per sample)"}
+                "note": ("integer-multiply bound, not HBM bound: 15 IMAD per band-sample on the half-rate IMAD pipe (DESIGN.md K2)" if q else
+                         "FP32-issue bound, not HBM bound: see DESIGN.md (60 FMA-pipe lane-ops per sample)")}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:

@@ -640,19 +640,14 @@ chain_outpost_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp, 
     }
 }
 
-// The delay rings take the last <= 4096 post-gain samples of a call (older writes of the call would have been overwritten
-// anyway): frames [Ta, Tb) of them per launch, any time after the output rows of those frames are final.  The launch with
-// `final` set also advances the shared write index.  Writing frame f while later frames are still being emitted is safe:
-// frame T > f reads history only at T - dl < 0, which lives at ring position f only if f - (T - dl) is a multiple of 4096,
-// and 0 < f - T + dl < 4096.
+// once per call, after every outpost launch of the call: the delay rings take the last <= 4096 post-gain
+// samples (older writes of this call would have been overwritten anyway), the shared write index advances
 __global__ void __launch_bounds__(256)
-chain_ring_kernel(ChainDev d, uint32_t Ta, uint32_t Tb, uint32_t F, uint32_t fpp, uint32_t final)
+chain_ring_kernel(ChainDev d, uint32_t F, uint32_t fpp)
 {
     const int lane = threadIdx.x & 31;
     const uint64_t units = (uint64_t)d.N * kOuts;
     const uint32_t Np = d.N_pad;
-    const uint32_t keep_from = F > (uint32_t)kMaxDelay ? F - kMaxDelay : 0u;
-    if (Ta < keep_from) Ta = keep_from;
     for (uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
         const uint32_t inst = (uint32_t)(u / kOuts), o = (uint32_t)(u % kOuts);
         const bool any_delay = d.flags[inst] & F_ANY_DELAY;
@@ -660,10 +655,10 @@ chain_ring_kernel(ChainDev d, uint32_t Ta, uint32_t Tb, uint32_t F, uint32_t fpp
         const OutCfg c = out_cfg(d, o, inst, any_delay, fpp);
         if (c.delay_on) {                                                    // outputs without delay never touch their ring
             float *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;
-            for (uint32_t T = Ta + lane; T < Tb; T += 32)
+            for (uint32_t T = (F > (uint32_t)kMaxDelay ? F - kMaxDelay : 0u) + lane; T < F; T += 32)
                 ring[(widx0 + T) & (kMaxDelay - 1)] = out_gain(c.row[T], c.enabled, gain_at(c, T));
         }
-        if (final && o == 0 && lane == 0) d.widx_out[inst] = any_delay ? (widx0 + F) & (kMaxDelay - 1) : widx0;   // :911, once per packet
+        if (o == 0 && lane == 0) d.widx_out[inst] = any_delay ? (widx0 + F) & (kMaxDelay - 1) : widx0;   // :911, once per packet
     }
 }
 
@@ -813,15 +808,8 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
     const ChainDev d = c->d;
     const uint32_t n_sms = st.rest_sms ? st.rest_sms : 148;     // SMs the streaming stages run on (chain_streams.cuh)
     static const uint32_t kStreamCtas = [] { const char *e = getenv("DSPI_CHAIN_CTAS"); const int v = e ? atoi(e) : 0; return (uint32_t)(v >= 1 && v <= 8 ? v : 8); }();   // streaming CTAs (256 threads) per SM
-    const unsigned place = dspi::ChainStreams::placement();
-    const uint32_t aux_sms = st.pdm_sms ? st.pdm_sms : 148;     // SMs s_mix / s_post run on
-    const bool ring_per_slice = place & 1u;
-    const cudaStream_t out_stream_of_slice = (place & 4u) ? st.s_post : st.s_out;
-    const cudaStream_t ring_stream = (place & 2u) ? st.s_post : out_stream_of_slice;
-    const uint32_t keep_from = F > (uint32_t)dspi::kMaxDelay ? F - dspi::kMaxDelay : 0u;
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
     CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
-    for (cudaStream_t s2 : { st.s_mix, st.s_post }) CU_OK(cudaStreamWaitEvent(s2, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t p0 = slice_bounds[sl], p1 = slice_bounds[sl + 1];
         const uint32_t fb = p0 * fpp, fe = p1 * fpp;
@@ -833,43 +821,25 @@ int launch_chain(dspi_chain *c, const void *d_pcm, uint32_t bit_depth, uint32_t 
         post<<<(d.N_pad / 16 + 3) / 4, 128, post_smem, st.s_front>>>(d, p0, p1 - p0, fpp);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_front[sl], st.s_front));
-        // ---- outputs: matrix -> per-output EQ (K1) -> gain / delay / metering / conversion (+ this slice's share of the rings)
-        const bool last_slice = sl + 1 == n_slices;
-        if (place & 4u) {                                                     // streaming stages beside the modulator (chain_streams.cuh)
-            CU_OK(cudaStreamWaitEvent(st.s_mix, st.ev_front[sl], 0));
-            dspi::chain_mix_kernel<FUSED><<<aux_sms * kStreamCtas, 256, 0, st.s_mix>>>(d, fb, fe);
-            CU_OK(cudaGetLastError());
-            CU_OK(cudaEventRecord(st.ev_mix[sl], st.s_mix));
-            CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_mix[sl], 0));
-            if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
-            CU_OK(cudaEventRecord(st.ev_eqo[sl], st.s_out));
-            CU_OK(cudaStreamWaitEvent(st.s_post, st.ev_eqo[sl], 0));
-            dspi::chain_outpost_kernel<<<aux_sms * kStreamCtas, 256, 0, st.s_post>>>(d, p0, p1 - p0, fpp, F, d_spdif);
-            CU_OK(cudaGetLastError());
-            CU_OK(cudaEventRecord(st.ev_out[sl], st.s_post));
-        } else {
-            CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
-            dspi::chain_mix_kernel<FUSED><<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, fb, fe);
-            CU_OK(cudaGetLastError());
-            if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
-            dspi::chain_outpost_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
-            CU_OK(cudaGetLastError());
-            CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
-        }
-        if (ring_per_slice ? (fe > keep_from || last_slice) : last_slice) {
-            if (ring_stream != out_stream_of_slice) CU_OK(cudaStreamWaitEvent(ring_stream, st.ev_out[sl], 0));
-            dspi::chain_ring_kernel<<<(ring_stream == st.s_out ? n_sms : aux_sms) * kStreamCtas, 256, 0, ring_stream>>>(d, ring_per_slice ? fb : 0u, fe, F, fpp, last_slice ? 1u : 0u);
-            CU_OK(cudaGetLastError());
-            c->launches++;
-        }
+        // ---- outputs: matrix -> per-output EQ (K1) -> gain / delay / metering / conversion
+        CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
+        dspi::chain_mix_kernel<FUSED><<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, fb, fe);
+        CU_OK(cudaGetLastError());
+        if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
+        dspi::chain_outpost_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        CU_OK(cudaGetLastError());
+        CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
         // ---- modulator
         CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
         dspi::chain_pdm_kernel<<<(d.N + 127) / 128, 128, 0, st.s_pdm>>>(d, fb, fe, F, d_pdm);
         CU_OK(cudaGetLastError());
         c->launches += 5;
     }
+    dspi::chain_ring_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, F, fpp);     // after the last outpost launch (stream order)
+    CU_OK(cudaGetLastError());
+    c->launches++;
     std::swap(c->d.widx_in, c->d.widx_out);
-    CU_OK(cudaEventRecord(st.ev_aux, ring_stream));                          // ring update done (and every output-stage launch before it)
+    CU_OK(cudaEventRecord(st.ev_aux, st.s_out));                             // ring update done
     CU_OK(cudaStreamWaitEvent(c->stream, st.ev_aux, 0));
     // the last modulator launch is ordered after every other stage launch of this call
     CU_OK(cudaEventRecord(st.ev_done, st.s_pdm));

@@ -592,16 +592,12 @@ chainq_outpost_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp, u
     }
 }
 
-// frames [Ta, Tb) of the call's last <= 4096 post-gain samples go into the delay rings; `final` advances the write index
-// (see chain_ring_kernel in chain_f32.cu for why this may run while later frames are still being emitted)
 __global__ void __launch_bounds__(256)
-chainq_ring_kernel(ChainQ d, uint32_t Ta, uint32_t Tb, uint32_t F, uint32_t fpp, uint32_t final)
+chainq_ring_kernel(ChainQ d, uint32_t F, uint32_t fpp)
 {
     const int lane = threadIdx.x & 31;
     const uint64_t units = (uint64_t)d.N * kOuts;
     const size_t Np = d.N_pad;
-    const uint32_t keep_from = F > (uint32_t)kMaxDelay ? F - kMaxDelay : 0u;
-    if (Ta < keep_from) Ta = keep_from;
     for (uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < units; u += (uint64_t)gridDim.x * (blockDim.x >> 5)) {
         const uint32_t inst = (uint32_t)(u / kOuts), o = (uint32_t)(u % kOuts);
         const bool any_delay = d.flags[inst] & F_ANY_DELAY;
@@ -609,10 +605,10 @@ chainq_ring_kernel(ChainQ d, uint32_t Ta, uint32_t Tb, uint32_t F, uint32_t fpp,
         const OutCfgQ c = outq_cfg(d, o, inst, any_delay, fpp);
         if (c.delay_on) {
             int32_t *ring = d.dline + ((size_t)o * Np + inst) * kMaxDelay;
-            for (uint32_t T = Ta + lane; T < Tb; T += 32)
+            for (uint32_t T = (F > (uint32_t)kMaxDelay ? F - kMaxDelay : 0u) + lane; T < F; T += 32)
                 ring[(widx0 + T) & (kMaxDelay - 1)] = outq_gain(c.row[T], c.enabled, gainq_at(c, T));
         }
-        if (final && o == 0 && lane == 0) d.widx_out[inst] = any_delay ? (widx0 + F) & (kMaxDelay - 1) : widx0;
+        if (o == 0 && lane == 0) d.widx_out[inst] = any_delay ? (widx0 + F) & (kMaxDelay - 1) : widx0;
     }
 }
 
@@ -1142,15 +1138,8 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
     const ChainQ d = c->d;
     const uint32_t n_sms = st.rest_sms ? st.rest_sms : 148;     // SMs the streaming stages run on (chain_streams.cuh)
     static const uint32_t kStreamCtas = [] { const char *e = getenv("DSPI_CHAIN_CTAS"); const int v = e ? atoi(e) : 0; return (uint32_t)(v >= 1 && v <= 8 ? v : 8); }();   // streaming CTAs (256 threads) per SM
-    const unsigned place = dspi::ChainStreams::placement();
-    const uint32_t aux_sms = st.pdm_sms ? st.pdm_sms : 148;     // SMs s_mix / s_post run on
-    const bool ring_per_slice = place & 1u;
-    const cudaStream_t out_stream_of_slice = (place & 4u) ? st.s_post : st.s_out;
-    const cudaStream_t ring_stream = (place & 2u) ? st.s_post : out_stream_of_slice;
-    const uint32_t keep_from = F > (uint32_t)dspi::kMaxDelay ? F - dspi::kMaxDelay : 0u;
     CU_OK(cudaEventRecord(st.ev_begin, c->stream));
     CU_OK(cudaStreamWaitEvent(st.s_front, st.ev_begin, 0));
-    for (cudaStream_t s2 : { st.s_mix, st.s_post }) CU_OK(cudaStreamWaitEvent(s2, st.ev_begin, 0));
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t p0 = slice_bounds[sl], p1 = slice_bounds[sl + 1];
         const uint32_t fb = p0 * fpp, fe = p1 * fpp;
@@ -1161,41 +1150,23 @@ int dspi_chainq_process_device(dspi_chainq *c, const void *d_pcm, uint32_t bit_d
         dspi::chainq_post_kernel<<<(d.N_pad / 16 + 3) / 4, 128, post_smem, st.s_front>>>(d, p0, p1 - p0, fpp);
         CU_OK(cudaGetLastError());
         CU_OK(cudaEventRecord(st.ev_front[sl], st.s_front));
-        const bool last_slice = sl + 1 == n_slices;
-        if (place & 4u) {                                                     // streaming stages beside the modulator (chain_streams.cuh)
-            CU_OK(cudaStreamWaitEvent(st.s_mix, st.ev_front[sl], 0));
-            dspi::chainq_mix_kernel<<<aux_sms * kStreamCtas, 256, 0, st.s_mix>>>(d, fb, fe);
-            CU_OK(cudaGetLastError());
-            CU_OK(cudaEventRecord(st.ev_mix[sl], st.s_mix));
-            CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_mix[sl], 0));
-            if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
-            CU_OK(cudaEventRecord(st.ev_eqo[sl], st.s_out));
-            CU_OK(cudaStreamWaitEvent(st.s_post, st.ev_eqo[sl], 0));
-            dspi::chainq_outpost_kernel<<<aux_sms * kStreamCtas, 256, 0, st.s_post>>>(d, p0, p1 - p0, fpp, F, d_spdif);
-            CU_OK(cudaGetLastError());
-            CU_OK(cudaEventRecord(st.ev_out[sl], st.s_post));
-        } else {
-            CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
-            dspi::chainq_mix_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, fb, fe);
-            CU_OK(cudaGetLastError());
-            if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
-            dspi::chainq_outpost_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
-            CU_OK(cudaGetLastError());
-            CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
-        }
-        if (ring_per_slice ? (fe > keep_from || last_slice) : last_slice) {
-            if (ring_stream != out_stream_of_slice) CU_OK(cudaStreamWaitEvent(ring_stream, st.ev_out[sl], 0));
-            dspi::chainq_ring_kernel<<<(ring_stream == st.s_out ? n_sms : aux_sms) * kStreamCtas, 256, 0, ring_stream>>>(d, ring_per_slice ? fb : 0u, fe, F, fpp, last_slice ? 1u : 0u);
-            CU_OK(cudaGetLastError());
-            c->launches++;
-        }
+        CU_OK(cudaStreamWaitEvent(st.s_out, st.ev_front[sl], 0));
+        dspi::chainq_mix_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, fb, fe);
+        CU_OK(cudaGetLastError());
+        if ((rc = dspi::eq_process_on(c->eq_o, d.orow + fb, fe - fb, d.ldF, st.s_out)) != DSPI_OK) return rc;
+        dspi::chainq_outpost_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, p0, p1 - p0, fpp, F, d_spdif);
+        CU_OK(cudaGetLastError());
+        CU_OK(cudaEventRecord(st.ev_out[sl], st.s_out));
         CU_OK(cudaStreamWaitEvent(st.s_pdm, st.ev_out[sl], 0));
         dspi::chainq_pdm_kernel<<<(d.N + 127) / 128, 128, 0, st.s_pdm>>>(d, fb, fe, F, d_pdm);
         CU_OK(cudaGetLastError());
         c->launches += 5;
     }
+    dspi::chainq_ring_kernel<<<n_sms * kStreamCtas, 256, 0, st.s_out>>>(d, F, fpp);            // after the last outpost launch (stream order)
+    CU_OK(cudaGetLastError());
+    c->launches++;
     std::swap(c->d.widx_in, c->d.widx_out);
-    CU_OK(cudaEventRecord(st.ev_aux, ring_stream));
+    CU_OK(cudaEventRecord(st.ev_aux, st.s_out));
     CU_OK(cudaStreamWaitEvent(c->stream, st.ev_aux, 0));
     CU_OK(cudaEventRecord(st.ev_done, st.s_pdm));
     CU_OK(cudaStreamWaitEvent(c->stream, st.ev_done, 0));

@@ -94,24 +94,9 @@ struct ChainStreams {
         return n;
     }
     cudaStream_t s_front = nullptr, s_out = nullptr, s_pdm = nullptr;
-    cudaStream_t s_mix = nullptr, s_post = nullptr;           // streaming stages, on the modulator's SMs when the GPU is partitioned (see placement())
     cudaEvent_t ev_begin = nullptr, ev_done = nullptr, ev_aux = nullptr, ev_front[kMaxSlices] = {}, ev_out[kMaxSlices] = {};
-    cudaEvent_t ev_mix[kMaxSlices] = {}, ev_eqo[kMaxSlices] = {};
     CUgreenCtx g_pdm = nullptr, g_rest = nullptr;
     unsigned pdm_sms = 0, rest_sms = 0;                       // 0: no partition (priority streams on the whole GPU)
-
-    // Where the streaming stages run (DSPI_CHAIN_PLACE, bit mask):
-    //   1  the delay rings are refreshed slice by slice (right after the slice's output stage) instead of once at the end of the call
-    //   2  ... on s_post instead of the output stream
-    //   4  matrix mix and output stage run on s_mix / s_post, i.e. on the modulator's SMs when the GPU is partitioned: one warp per
-    //      scheduler leaves those SMs' load/store units, registers and most issue slots idle, while the other partition is what the
-    //      call waits for
-    static unsigned placement()
-    {
-        static const unsigned v = [] { const char *e = getenv("DSPI_CHAIN_PLACE"); return e ? (unsigned)atoi(e) : kDefaultPlacement; }();
-        return v;
-    }
-    static constexpr unsigned kDefaultPlacement = 0;
 
     // modulator CTAs are 128 threads (one warp per sub-partition): ceil(instances / 128) SMs, in the partition granularity of 8
     static unsigned wanted_pdm_sms(unsigned n_instances)
@@ -134,15 +119,14 @@ struct ChainStreams {
         if (ga.DevResourceGenerateDesc(&d_part, &part, 1) != CUDA_SUCCESS || ga.DevResourceGenerateDesc(&d_rest, &rest, 1) != CUDA_SUCCESS) return false;
         if (ga.GreenCtxCreate(&g_pdm, d_part, (CUdevice)device, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g_pdm = nullptr; return false; }
         if (ga.GreenCtxCreate(&g_rest, d_rest, (CUdevice)device, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) { g_rest = nullptr; destroy_partition(); return false; }
-        CUstream a = nullptr, b = nullptr, c = nullptr, m = nullptr, o = nullptr;
+        CUstream a = nullptr, b = nullptr, c = nullptr;
         if (ga.GreenCtxStreamCreate(&a, g_pdm, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS || ga.GreenCtxStreamCreate(&b, g_rest, CU_STREAM_NON_BLOCKING, prio_mid) != CUDA_SUCCESS ||
-            ga.GreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS || ga.GreenCtxStreamCreate(&m, g_pdm, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS ||
-            ga.GreenCtxStreamCreate(&o, g_pdm, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) {
-            for (CUstream st : { a, b, c, m, o }) if (st) cudaStreamDestroy((cudaStream_t)st);
+            ga.GreenCtxStreamCreate(&c, g_rest, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) {
+            for (CUstream st : { a, b, c }) if (st) cudaStreamDestroy((cudaStream_t)st);
             destroy_partition();
             return false;
         }
-        s_pdm = (cudaStream_t)a; s_front = (cudaStream_t)b; s_out = (cudaStream_t)c; s_mix = (cudaStream_t)m; s_post = (cudaStream_t)o;
+        s_pdm = (cudaStream_t)a; s_front = (cudaStream_t)b; s_out = (cudaStream_t)c;
         pdm_sms = part.sm.smCount; rest_sms = rest.sm.smCount;
         return true;
     }
@@ -169,8 +153,6 @@ struct ChainStreams {
             if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_pdm, cudaStreamNonBlocking, hi);
             if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_front, cudaStreamNonBlocking, mid);
             if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_out, cudaStreamNonBlocking, lo);
-            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_mix, cudaStreamNonBlocking, lo);
-            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s_post, cudaStreamNonBlocking, lo);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_begin, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming);
@@ -178,15 +160,13 @@ struct ChainStreams {
         for (int i = 0; i < kMaxSlices && e == cudaSuccess; i++) {
             e = cudaEventCreateWithFlags(&ev_front[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_mix[i], cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_eqo[i], cudaEventDisableTiming);
         }
         return e;
     }
 
     void destroy()
     {
-        for (cudaStream_t *s : { &s_front, &s_out, &s_pdm, &s_mix, &s_post })
+        for (cudaStream_t *s : { &s_front, &s_out, &s_pdm })
             if (*s) { cudaStreamSynchronize(*s); cudaStreamDestroy(*s); *s = nullptr; }
         destroy_partition();
         for (cudaEvent_t *ev : { &ev_begin, &ev_done, &ev_aux })
@@ -194,8 +174,6 @@ struct ChainStreams {
         for (int i = 0; i < kMaxSlices; i++) {
             if (ev_front[i]) { cudaEventDestroy(ev_front[i]); ev_front[i] = nullptr; }
             if (ev_out[i]) { cudaEventDestroy(ev_out[i]); ev_out[i] = nullptr; }
-            if (ev_mix[i]) { cudaEventDestroy(ev_mix[i]); ev_mix[i] = nullptr; }
-            if (ev_eqo[i]) { cudaEventDestroy(ev_eqo[i]); ev_eqo[i] = nullptr; }
         }
     }
 };
