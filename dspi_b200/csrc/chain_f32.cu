@@ -275,6 +275,23 @@ chain_post_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
         cp_async_wait_all();
         __syncwarp();
 
+        // ---- PASS 3 for one sample: input peak, then crossfeed (usb_audio.c:741-749); every lane walks the same shuffle ----
+        float pk = 0.0f;
+        auto peak_and_crossfeed = [&](uint32_t i, float v) {
+            const float a = fabsf(v);
+            if (a > pk) pk = a;
+            float lp = 0.0f, ap = 0.0f;
+            if (xf_on) {
+                lp = fm<FUSED>(xf_a0, v, __fmul_rn(xf_b1, xf_lp));           // crossfeed.c:137-138
+                xf_lp = lp;
+                ap = fm<FUSED>(xf_ap, lp, xf_as);                            // :146 / :148
+                xf_as = fnm<FUSED>(xf_ap, ap, lp);                           // :147 / :149
+            }
+            const float ap_other = __shfl_xor_sync(0xffffffffu, ap, 16);
+            if (xf_on) v = __fadd_rn(__fadd_rn(v, -lp), ap_other);           // :154-155
+            xs[i * kXs] = v;
+        };
+
         // ---- PASS 2.5: leveller ----
         if (__any_sync(0xffffffffu, lev_on)) {
             const float a_rms = lvc[0], one_minus = __fadd_rn(1.0f, -a_rms);
@@ -305,8 +322,11 @@ chain_post_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
             float gain, gain_step;
             if (fpp == 1) { gain = new_gain; gain_step = 0.0f; }
             else { gain_step = __fdiv_rn(__fadd_rn(new_gain, -prev_for_ramp), (float)(fpp - 1)); gain = prev_for_ramp; }
-            for (uint32_t i = 0; i < fpp; i++) {                             // :228-259
-                float o = xs[i * kXs];
+            // the leveller's per-sample part and PASS 3 share one loop: ramp, look-ahead exchange and peak limit of sample
+            // i+1 do not depend on the crossfeed recurrence of sample i, so the serial chains overlap
+            for (uint32_t i = 0; i < fpp; i++) {                             // :228-259, then usb_audio.c:741-749
+                const float x0 = xs[i * kXs];
+                float o = x0;
                 if (lev_on && lookahead) {
                     const float held = hs[i * kXs];
                     la_buf[(size_t)la_idx * Np] = o;
@@ -324,8 +344,8 @@ chain_post_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
                     const float max_g = __fdiv_rn(0.70795f, peak);
                     if (max_g < g) g = (max_g > 1.0f) ? max_g : 1.0f;
                 }
-                if (lev_on) xs[i * kXs] = __fmul_rn(o, g);
                 gain = __fadd_rn(gain, gain_step);
+                peak_and_crossfeed(i, lev_on ? __fmul_rn(o, g) : x0);
             }
             if (lev_on) {
                 env = e;
@@ -333,24 +353,8 @@ chain_post_kernel(ChainDev d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
                 gain_prev = gain_lin;
                 gain_lin = new_gain;
             }
-        }
-
-        // ---- PASS 3: input peaks, then crossfeed (usb_audio.c:741-749) ----
-        float pk = 0.0f;
-        for (uint32_t i = 0; i < fpp; i++) {
-            float v = xs[i * kXs];
-            const float a = fabsf(v);
-            if (a > pk) pk = a;
-            float lp = 0.0f, ap = 0.0f;
-            if (xf_on) {
-                lp = fm<FUSED>(xf_a0, v, __fmul_rn(xf_b1, xf_lp));           // crossfeed.c:137-138
-                xf_lp = lp;
-                ap = fm<FUSED>(xf_ap, lp, xf_as);                            // :146 / :148
-                xf_as = fnm<FUSED>(xf_ap, ap, lp);                           // :147 / :149
-            }
-            const float ap_other = __shfl_xor_sync(0xffffffffu, ap, 16);
-            if (xf_on) v = __fadd_rn(__fadd_rn(v, -lp), ap_other);           // :154-155
-            xs[i * kXs] = v;
+        } else {
+            for (uint32_t i = 0; i < fpp; i++) peak_and_crossfeed(i, xs[i * kXs]);
         }
         peak_in = pk;                                                        // peaks describe the last packet
         if (pk > 1.001f) clip |= (uint16_t)(1u << side);                     // config.h:53

@@ -237,6 +237,23 @@ chainq_post_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
         cp_async_wait_all();
         __syncwarp();
 
+        // PASS 3 (:1065-1073) for one sample: input peak, crossfeed (every lane walks the same shuffle)
+        int32_t pk = 0;
+        auto peak_and_crossfeed = [&](uint32_t i, int32_t v) {
+            const int32_t a = abs(v);
+            if (a > pk) pk = a;
+            int32_t lp = 0, ap = 0;
+            if (xf_on) {
+                lp = mul_q28(xf_a0, v) + mul_q28(xf_b1, xf_lp);                                           // crossfeed.c:166-167
+                xf_lp = lp;
+                ap = mul_q28(xf_ap, lp) + xf_as;                                                          // :172
+                xf_as = lp - mul_q28(xf_ap, ap);                                                          // :173
+            }
+            const int32_t ap_other = __shfl_xor_sync(0xffffffffu, ap, 16);
+            if (xf_on) v = (v - lp) + ap_other;                                                           // :178-179
+            xs[i * kXs] = v;
+        };
+
         // PASS 2.5: leveller (leveller.c:275-389); every lane walks the same shuffles
         if (__any_sync(0xffffffffu, lev_on)) {
             const int32_t a_rms = __float2int_rz(__fmul_rn(lvc[0], 268435456.0f));                       // :286
@@ -265,17 +282,25 @@ chainq_post_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
             const float gl = (float)pow(10.0, (double)__fdiv_rn(new_smooth, 20.0f));                      // :332
             const int32_t g_cur = __float2int_rz(__fmul_rn(gl, 268435456.0f));                            // :334 (saturating)
             const int32_t g_prev = gain_q;
-            // :352 divides a 64-bit product by (fpp - 1) per sample.  |product| < 2^39 and the divisor is < 192, so the
-            // correctly rounded double quotient can never cross an integer (it is at least 1/191 away from the next one
-            // unless exact, the rounding error is below 2^-13): truncating it IS the int64 quotient, without the
-            // ~100-instruction 64-bit division routine in the per-sample loop.
-            const double inv_den = fpp > 1 ? (double)(int32_t)(fpp - 1) : 1.0;
-            const double g_diff = (double)(int32_t)((uint32_t)g_cur - (uint32_t)g_prev);            // the int32 difference of :352
-            for (uint32_t i = 0; i < fpp; i++) {                                                          // :347-386
-                int32_t gain;
-                if (fpp == 1) gain = g_cur;
-                else gain = g_prev + (int32_t)(int64_t)__ddiv_rn(g_diff * (double)i, inv_den);           // :352
-                int32_t o = xs[i * kXs];
+            // :352 is gain = prev + (int32)((int64)(cur - prev) * i / (fpp - 1)) per sample (C division: towards zero).  With
+            // diff = Q * D + R (D = fpp - 1, R with the sign of diff, |R| < D) the quotient is Q * i + trunc(R * i / D), both terms
+            // of one sign, so it is carried incrementally: off += Q, acc += R, one correction when |acc| reaches D.  All in
+            // 32-bit wrapping arithmetic, which is the int32 cast of :352; no 64-bit division in the per-sample loop.
+            const int32_t g_diff = (int32_t)((uint32_t)g_cur - (uint32_t)g_prev);
+            const int32_t den = fpp > 1 ? (int32_t)(fpp - 1) : 1;
+            const int32_t ramp_q = g_diff / den, ramp_r = g_diff - ramp_q * den;
+            uint32_t off = 0;
+            int32_t acc = 0;
+            // The leveller's per-sample part and PASS 3 share one loop: the ramp, the look-ahead exchange and the peak limit of
+            // sample i+1 do not depend on the crossfeed recurrence of sample i, so the two serial chains overlap.
+            for (uint32_t i = 0; i < fpp; i++) {                                                          // :347-386, :1065-1073
+                int32_t gain = fpp == 1 ? g_cur : (int32_t)((uint32_t)g_prev + off);                      // :352
+                off += (uint32_t)ramp_q;
+                acc += ramp_r;
+                if (acc >= den) { acc -= den; off++; }
+                else if (acc <= -den) { acc += den; off--; }
+                const int32_t x0 = xs[i * kXs];
+                int32_t o = x0;
                 if (lev_on && lookahead) {
                     const int32_t held = hs[i * kXs];
                     la_buf[(size_t)la_idx * Np] = o;
@@ -295,7 +320,7 @@ chainq_post_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
                         if (max_g < gain) gain = (max_g > kUnity) ? max_g : kUnity;
                     }
                 }
-                if (lev_on) xs[i * kXs] = mul_q28(o, gain);
+                peak_and_crossfeed(i, lev_on ? mul_q28(o, gain) : x0);
             }
             if (lev_on) {
                 env = e;
@@ -303,24 +328,8 @@ chainq_post_kernel(ChainQ d, uint32_t p0, uint32_t n_packets, uint32_t fpp)
                 gain_prev_q = g_prev;
                 gain_q = g_cur;
             }
-        }
-
-        // PASS 3 (:1065-1073)
-        int32_t pk = 0;
-        for (uint32_t i = 0; i < fpp; i++) {
-            int32_t v = xs[i * kXs];
-            const int32_t a = abs(v);
-            if (a > pk) pk = a;
-            int32_t lp = 0, ap = 0;
-            if (xf_on) {
-                lp = mul_q28(xf_a0, v) + mul_q28(xf_b1, xf_lp);                                           // crossfeed.c:166-167
-                xf_lp = lp;
-                ap = mul_q28(xf_ap, lp) + xf_as;                                                          // :172
-                xf_as = lp - mul_q28(xf_ap, ap);                                                          // :173
-            }
-            const int32_t ap_other = __shfl_xor_sync(0xffffffffu, ap, 16);
-            if (xf_on) v = (v - lp) + ap_other;                                                           // :178-179
-            xs[i * kXs] = v;
+        } else {
+            for (uint32_t i = 0; i < fpp; i++) peak_and_crossfeed(i, xs[i * kXs]);
         }
         peak_last = pk;
         if (pk > kClipThresh) clip |= (uint16_t)(1u << side);
