@@ -130,6 +130,40 @@ __device__ __forceinline__ uint32_t chunk(int32_t &err1, int32_t &err2, int32_t 
         word = ~inv;
         err2 = sv - dither;
         err1 = g2 - tg - target;                               // g2 = g + tg, g = err1 + target
+    } else if constexpr (V == 8 || V == 9) {
+        // speculative two-step look-ahead on the three sums of V7 (z = -m, K = 65535):
+        //   one step:  s' = t2 + 2K z;  t2' = (t2 + g2 - 2K) + 3K z;  g2' = (g2 + tg) + K z
+        //   the second comparator sees s' = t2 (z0 = 0) or t2 + 2K (z0 = 1): both signs are taken BEFORE z0 is known and one LOP3 selects
+        //   two steps: s'' = A + 3K z0 + 2K z1;  t2'' = B + 4K z0 + 3K z1;  g2'' = G + K z0 + K z1
+        //              A = t2 + g2 - 2K,  B = t2 + 2 g2 + tg - 4K,  G = g2 + 2 tg
+        // chain per PAIR of decisions: shift -> select -> IMAD (V9 carries u2 = t2 + 2K as a fourth sum so that its sign needs no add first)
+        int32_t sv = err2 + dither;
+        const int32_t g0 = err1 + target, tg = target - 65535;
+        int32_t t2 = sv + g0 - 131070, g2 = g0 + tg, u2 = t2 + 131070;
+        const int32_t cB = tg - 131070, tg2 = 2 * tg;
+        uint32_t inv = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+            const int32_t m0 = sv >> 31;
+            const int32_t ma = t2 >> 31;
+            const int32_t mb = (V == 9 ? u2 : t2 + 131070) >> 31;
+            const int32_t A = t2 + g2 - 131070;
+            const int32_t B = A + g2 + cB;
+            const int32_t G = g2 + tg2;
+            inv = __funnelshift_l((uint32_t)sv, inv, 1);
+            const int32_t m1 = (m0 & mb) | (~m0 & ma);
+            const int32_t pS = m0 * -196605 + A;
+            const int32_t pT = m0 * -262140 + B;
+            const int32_t pG = m0 * -65535 + G;
+            inv = __funnelshift_l((uint32_t)m1, inv, 1);
+            sv = m1 * -131070 + pS;
+            t2 = m1 * -196605 + pT;
+            g2 = m1 * -65535 + pG;
+            if (V == 9) u2 = m1 * -196605 + (pT + 131070);
+        }
+        word = ~inv;
+        err2 = sv - dither;
+        err1 = g2 - tg - target;
     }
     return word;
 }
@@ -225,6 +259,8 @@ int main()
         run<5>("imad two-sum, lop3 word", st, out, cyc, w);
         run<6>("fp32 saturating-add two-sum", st, out, cyc, w);
         run<7>("imad three-sum", st, out, cyc, w);
+        run<8>("two-step look-ahead, 3 sums", st, out, cyc, w);
+        run<9>("two-step look-ahead, 4 sums", st, out, cyc, w);
     }
     return 0;
 }
