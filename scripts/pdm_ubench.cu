@@ -130,6 +130,28 @@ __device__ __forceinline__ uint32_t chunk(int32_t &err1, int32_t &err2, int32_t 
         word = ~inv;
         err2 = sv - dither;
         err1 = g2 - tg - target;                               // g2 = g + tg, g = err1 + target
+    } else if constexpr (V == 10) {
+        // V7 with the sign mask taken on the FMA pipe too (mul.hi.s32 by 1 = s >> 31): no pipe crossing in the chain
+        int32_t sv = err2 + dither;
+        const int32_t g0 = err1 + target, tg = target - 65535;
+        int32_t t2 = sv + g0 - 131070, g2 = g0 + tg;
+        uint32_t inv = 0;
+        int32_t one;
+        asm volatile("mov.s32 %0, 1;" : "=r"(one));
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            int32_t m;
+            asm("mul.hi.s32 %0, %1, %2;" : "=r"(m) : "r"(sv), "r"(one));
+            const int32_t a = t2 + g2 - 131070;
+            const int32_t b = g2 + tg;
+            inv = __funnelshift_l((uint32_t)sv, inv, 1);
+            sv = m * -131070 + t2;
+            t2 = m * -196605 + a;
+            g2 = m * -65535 + b;
+        }
+        word = ~inv;
+        err2 = sv - dither;
+        err1 = g2 - tg - target;
     } else if constexpr (V == 8 || V == 9) {
         // speculative two-step look-ahead on the three sums of V7 (z = -m, K = 65535):
         //   one step:  s' = t2 + 2K z;  t2' = (t2 + g2 - 2K) + 3K z;  g2' = (g2 + tg) + K z
@@ -259,6 +281,7 @@ int main()
         run<5>("imad two-sum, lop3 word", st, out, cyc, w);
         run<6>("fp32 saturating-add two-sum", st, out, cyc, w);
         run<7>("imad three-sum", st, out, cyc, w);
+        run<10>("three-sum, sign by IMAD.HI", st, out, cyc, w);
         run<8>("two-step look-ahead, 3 sums", st, out, cyc, w);
         run<9>("two-step look-ahead, 4 sums", st, out, cyc, w);
     }
