@@ -58,7 +58,7 @@ def test_chain_uniform_config3_shape(oracle):
     _compare(oracle, "f32f", N=64, fs=96000.0, bit_depth=24, n_packets=10, fpp=96, seed=7, uniform=True)
 
 
-@pytest.mark.parametrize("fpp", [1, 47, 48, 192])
+@pytest.mark.parametrize("fpp", [1, 2, 47, 48, 192])
 def test_chain_packet_sizes(oracle, fpp):
     """leveller block gain, delay write index and peaks depend on the packet length"""
     _compare(oracle, "f32f", N=33, fs=48000.0, bit_depth=16, n_packets=6, fpp=fpp, seed=11)

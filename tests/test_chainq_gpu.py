@@ -48,7 +48,7 @@ def test_chainq_matches_oracle(oracle, bit_depth):
     _compare(oracle, N=70, fs=96000.0, bit_depth=bit_depth, n_packets=12, fpp=96, seed=300)
 
 
-@pytest.mark.parametrize("fpp", [1, 47, 48, 192])
+@pytest.mark.parametrize("fpp", [1, 2, 47, 48, 192])
 def test_chainq_packet_sizes(oracle, fpp):
     _compare(oracle, N=33, fs=48000.0, bit_depth=16, n_packets=6, fpp=fpp, seed=311)
 

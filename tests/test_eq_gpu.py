@@ -85,6 +85,31 @@ def test_q28_cascade_bit_exact(oracle, variant):
     assert same_bits(st, wst)
 
 
+@pytest.mark.parametrize("n_bands", [1, 7, 10, 12])
+@pytest.mark.parametrize("shape", ["all_on", "mixed", "one_band_flat_everywhere"])
+def test_q28_band_counts_and_bypass_paths(oracle, n_bands, shape):
+    """K2 has three code paths per warp (eq_q28.cu): one straight-line block when every band of every lane runs, the same
+    block with selects when some lanes bypass a band, and the per-band branches when a band is flat in the whole warp or the
+    engine has fewer bands than the kernel's template.  Every (band count, bypass shape) pair lands on one of them; all must
+    be the firmware's arithmetic bit for bit (dsp_process_rp2040.S:225-394, bypass test :246-248)."""
+    fs, Cn, T = 48000.0, 96, 1000                       # 3 warps; T leaves a partial register tile at the end
+    params = W.eq_params("mixed" if shape == "mixed" else "A", Cn, fs=fs, nbands=n_bands, seed=21)
+    if shape == "one_band_flat_everywhere":
+        params["gain_db"][:, n_bands // 2] = 0.0
+        params["type"][:, n_bands // 2] = L.PEAKING
+    bq = api.compute_coefficients(params, q28=True, fs=fs)
+    if shape == "all_on":
+        assert not bq["bypass"][:, :n_bands].any()
+    if shape == "one_band_flat_everywhere":
+        assert bq["bypass"][:, n_bands // 2].all()
+    x = W.inputs_q28(Cn, T)
+    x[5] = np.random.default_rng(3).integers(-2**31, 2**31, T, dtype=np.int64).astype(np.int32)          # wrap-around stress
+    y, st = _run_gpu("q28", bq, x, n_bands=n_bands, splits=[504, 496])
+    want, wst = _oracle(oracle, "q28", bq, x, n_bands=n_bands)
+    assert np.array_equal(y, want)
+    assert same_bits(st, wst)
+
+
 @pytest.mark.parametrize("flavour", ["f32f", "q28"])
 @pytest.mark.parametrize("Cn,T,ld", [(1, 1, 4), (2, 48, 48), (100, 1004, 1004), (65, 1003, 1003), (130, 96, 200), (64, 33, 36)])
 def test_ragged_shapes(oracle, flavour, Cn, T, ld):

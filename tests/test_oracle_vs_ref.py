@@ -147,7 +147,7 @@ def test_crossfeed(oracle, refs, flavour, preset):
 
 @pytest.mark.parametrize("flavour", ["f32s", "f32f", "q28"])
 @pytest.mark.parametrize("lookahead", [0, 1])
-@pytest.mark.parametrize("count", [1, 48, 96, 191])
+@pytest.mark.parametrize("count", [1, 2, 48, 96, 191])
 def test_leveller(oracle, refs, flavour, lookahead, count):
     fs = 96000.0
     q = flavour == "q28"
