@@ -595,7 +595,17 @@ int eq_process_remote_enqueue(dspi_eq *e, void *remote, uint32_t T, uint32_t ch0
     if (T == 0 || n_ch == 0) return DSPI_OK;
     CU_OK(cudaSetDevice(e->desc.device));
     const uint32_t ld = (T + 3) & ~3u;                                      // device rows padded for TMA
-    uint32_t cc = (uint32_t)(((size_t)96 << 20) / ((size_t)ld * 4));
+    // chunk size: the un-overlapped first copy-in and last copy-out of a call want it small, but a cascade kernel takes as long as
+    // its rows are long however few rows it gets (0.9 ms at 6144 frames), so chunks that copy faster than that make the kernel
+    // stream the bottleneck: 65536 ch x 6144 from pinned memory on B200 (profiles/r2_e2e_chunk_sweep.txt) 96 MiB 11.34, 64 MiB 11.49,
+    // 48 MiB 11.55, 32 MiB 8.03, 16 MiB 3.91 G samples/s.  DSPI_HOST_CHUNK_MB overrides.
+    // A peer GPU's memory arrives over NVLink an order of magnitude faster, so there the larger chunk stays.
+    static const size_t chunk_mb_env = [] { const char *v = getenv("DSPI_HOST_CHUNK_MB"); const long n = v ? atol(v) : 0; return (size_t)(n >= 1 && n <= 1024 ? n : 0); }();
+    cudaPointerAttributes pa;
+    const bool on_device = cudaPointerGetAttributes(&pa, remote) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const size_t chunk_mb = chunk_mb_env ? chunk_mb_env : (on_device ? 96 : 48);
+    uint32_t cc = (uint32_t)((chunk_mb << 20) / ((size_t)ld * 4));
     cc = cc / e->rows * e->rows;
     if (cc < e->rows) cc = e->rows;
     if (cc > e->c_pad) cc = e->c_pad;
