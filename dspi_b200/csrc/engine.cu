@@ -52,7 +52,7 @@ EncodeTiledFn encode_fn()
     return fn;
 }
 
-constexpr int kHostBufs = 3;
+constexpr int kHostBufs = 8;   // staging ring of the host / peer pipeline; each buffer has a kernel stream of its own
 
 }  // namespace
 
@@ -71,6 +71,8 @@ struct dspi_eq {
     uint32_t n_groups;
     uint32_t c_pad;          // n_groups * rows
     cudaStream_t stream, s_h2d, s_d2h;
+    cudaStream_t s_k[kHostBufs];   // chunk kernels of the staged pipeline (eq_process_remote_enqueue)
+    cudaEvent_t ev_begin;
     void *d_aos;             // Biquad[c_pad][12] in the reference layout (device mirror)
     void *d_coef;            // packed coefficient + state store
     uint64_t *d_modes;       // float only: per-channel topology words as packed from the coefficient structs
@@ -203,7 +205,9 @@ int dspi_eq_create(dspi_eq **out, const dspi_eq_desc *desc)
     if ((err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess) goto cuda_fail;
     if ((err = cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) goto cuda_fail;
     if ((err = cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) goto cuda_fail;
+    if ((err = cudaEventCreateWithFlags(&e->ev_begin, cudaEventDisableTiming)) != cudaSuccess) goto cuda_fail;
     for (int i = 0; i < kHostBufs; i++) {
+        if ((err = cudaStreamCreateWithFlags(&e->s_k[i], cudaStreamNonBlocking)) != cudaSuccess) goto cuda_fail;
         if ((err = cudaEventCreateWithFlags(&e->ev_in[i], cudaEventDisableTiming)) != cudaSuccess) goto cuda_fail;
         if ((err = cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming)) != cudaSuccess) goto cuda_fail;
         if ((err = cudaEventCreateWithFlags(&e->ev_out[i], cudaEventDisableTiming)) != cudaSuccess) goto cuda_fail;
@@ -237,6 +241,7 @@ int dspi_eq_destroy(dspi_eq *e)
     if (e->s_h2d) cudaStreamSynchronize(e->s_h2d);
     if (e->s_d2h) cudaStreamSynchronize(e->s_d2h);
     for (int i = 0; i < kHostBufs; i++) {
+        if (e->s_k[i]) { cudaStreamSynchronize(e->s_k[i]); cudaStreamDestroy(e->s_k[i]); }
         if (e->d_stage[i]) cudaFree(e->d_stage[i]);
         if (e->ev_in[i]) cudaEventDestroy(e->ev_in[i]);
         if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
@@ -250,6 +255,7 @@ int dspi_eq_destroy(dspi_eq *e)
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->s_h2d) cudaStreamDestroy(e->s_h2d);
     if (e->s_d2h) cudaStreamDestroy(e->s_d2h);
+    if (e->ev_begin) cudaEventDestroy(e->ev_begin);
     delete e;
     cudaGetLastError();
     return DSPI_OK;
@@ -586,25 +592,28 @@ int dspi_eq_process_device_range(dspi_eq *e, void *d_rows, uint32_t T, uint32_t 
 
 // The staged pipeline behind dspi_eq_process_host and the multi-device group (eqx.cu): rows [c0, c1) x T are contiguous in
 // the caller's [C][T] array, so every copy is one large 1-D transfer at full link rate; copy-in, kernel and copy-out of
-// consecutive chunks overlap on three streams, which also keeps BOTH directions of the link busy.  `remote` may be pinned
-// host memory (PCIe) or memory of a peer GPU with peer access enabled (NVLink): cudaMemcpyDefault resolves either.
-// Channels are independent, so chunk order and size change no bit.  enqueue returns without waiting.
+// consecutive chunks overlap, which also keeps BOTH directions of the link busy.  `remote` may be pinned host memory (PCIe)
+// or memory of a peer GPU with peer access enabled (NVLink): cudaMemcpyDefault resolves either.
+// A cascade kernel takes as long as its rows are long however few rows it gets (parallel over channels, serial over time:
+// 0.9 ms for 6144 frames) while a chunk fills only a few SMs, so every staging buffer has a kernel stream of its own and the
+// kernels of consecutive chunks run side by side; one kernel stream would cap the pipeline at one chunk per kernel time
+// (profiles/r2_e2e_chunk_sweep.txt: 32 MiB chunks 8.0, 16 MiB 3.9 G samples/s that way, 11.2 and 11.4 with the streams), and
+// the ring is deep enough to cover copy + kernel + copy (kHostBufs).  Channels are independent, so chunk order and size change
+// no bit.  enqueue returns without waiting.
 namespace dspi {
 int eq_process_remote_enqueue(dspi_eq *e, void *remote, uint32_t T, uint32_t ch0, uint32_t n_ch)
 {
     if (T == 0 || n_ch == 0) return DSPI_OK;
     CU_OK(cudaSetDevice(e->desc.device));
     const uint32_t ld = (T + 3) & ~3u;                                      // device rows padded for TMA
-    // chunk size: the un-overlapped first copy-in and last copy-out of a call want it small, but a cascade kernel takes as long as
-    // its rows are long however few rows it gets (0.9 ms at 6144 frames), so chunks that copy faster than that make the kernel
-    // stream the bottleneck: 65536 ch x 6144 from pinned memory on B200 (profiles/r2_e2e_chunk_sweep.txt) 96 MiB 11.34, 64 MiB 11.49,
-    // 48 MiB 11.55, 32 MiB 8.03, 16 MiB 3.91 G samples/s.  DSPI_HOST_CHUNK_MB overrides.
-    // A peer GPU's memory arrives over NVLink an order of magnitude faster, so there the larger chunk stays.
+    // chunk bytes: from a peer GPU over NVLink a chunk should take about (kernel time) / (kHostBufs - 3) to copy: 128 MiB.  Over PCIe
+    // 48 MiB measures best (profiles/r2_e2e_chunk_sweep.txt: 11.6 G samples/s; 16 MiB 11.4, 8 MiB 9.9 - smaller copies cost link
+    // efficiency faster than they shorten the ends of the pipeline).  DSPI_HOST_CHUNK_MB overrides both.
     static const size_t chunk_mb_env = [] { const char *v = getenv("DSPI_HOST_CHUNK_MB"); const long n = v ? atol(v) : 0; return (size_t)(n >= 1 && n <= 1024 ? n : 0); }();
     cudaPointerAttributes pa;
     const bool on_device = cudaPointerGetAttributes(&pa, remote) == cudaSuccess && pa.type == cudaMemoryTypeDevice;
     cudaGetLastError();
-    const size_t chunk_mb = chunk_mb_env ? chunk_mb_env : (on_device ? 96 : 48);
+    const size_t chunk_mb = chunk_mb_env ? chunk_mb_env : (on_device ? 128 : 48);
     uint32_t cc = (uint32_t)((chunk_mb << 20) / ((size_t)ld * 4));
     cc = cc / e->rows * e->rows;
     if (cc < e->rows) cc = e->rows;
@@ -623,6 +632,7 @@ int eq_process_remote_enqueue(dspi_eq *e, void *remote, uint32_t T, uint32_t ch0
     }
     const uint32_t nchunks = (n_ch + cc - 1) / cc;
     char *base = (char *)remote;
+    CU_OK(cudaEventRecord(e->ev_begin, e->stream));                         // uploads / parameter changes queued on the engine stream come first
     for (uint32_t k = 0; k < nchunks; k++) {
         const int b = k % kHostBufs;
         const uint32_t c0 = k * cc, n = (n_ch - c0 < cc) ? (n_ch - c0) : cc;
@@ -631,15 +641,18 @@ int eq_process_remote_enqueue(dspi_eq *e, void *remote, uint32_t T, uint32_t ch0
         if (ld == T) CU_OK(cudaMemcpyAsync(e->d_stage[b], hp, (size_t)n * T * 4, cudaMemcpyDefault, e->s_h2d));
         else CU_OK(cudaMemcpy2DAsync(e->d_stage[b], (size_t)ld * 4, hp, (size_t)T * 4, (size_t)T * 4, n, cudaMemcpyDefault, e->s_h2d));
         CU_OK(cudaEventRecord(e->ev_in[b], e->s_h2d));
-        CU_OK(cudaStreamWaitEvent(e->stream, e->ev_in[b], 0));
-        int rc = launch_eq(e, e->d_stage[b], T, ld, (ch0 + c0) / e->rows, (n + e->rows - 1) / e->rows, n, e->stream);
+        if (k < (uint32_t)kHostBufs) CU_OK(cudaStreamWaitEvent(e->s_k[b], e->ev_begin, 0));
+        CU_OK(cudaStreamWaitEvent(e->s_k[b], e->ev_in[b], 0));
+        int rc = launch_eq(e, e->d_stage[b], T, ld, (ch0 + c0) / e->rows, (n + e->rows - 1) / e->rows, n, e->s_k[b]);
         if (rc) return rc;
-        CU_OK(cudaEventRecord(e->ev_done[b], e->stream));
+        CU_OK(cudaEventRecord(e->ev_done[b], e->s_k[b]));
         CU_OK(cudaStreamWaitEvent(e->s_d2h, e->ev_done[b], 0));
         if (ld == T) CU_OK(cudaMemcpyAsync(hp, e->d_stage[b], (size_t)n * T * 4, cudaMemcpyDefault, e->s_d2h));
         else CU_OK(cudaMemcpy2DAsync(hp, (size_t)T * 4, e->d_stage[b], (size_t)ld * 4, (size_t)T * 4, n, cudaMemcpyDefault, e->s_d2h));
         CU_OK(cudaEventRecord(e->ev_out[b], e->s_d2h));
     }
+    for (uint32_t b = 0; b < (uint32_t)kHostBufs && b < nchunks; b++)       // later work on the engine stream sees the new filter state
+        CU_OK(cudaStreamWaitEvent(e->stream, e->ev_done[b], 0));
     return DSPI_OK;
 }
 

@@ -294,3 +294,32 @@ def test_kernel_choice_reporting(monkeypatch):
         assert eng.kernel_info().startswith("aot q28")
     finally:
         eng.close()
+
+
+def test_host_path_many_small_chunks():
+    """dspi_eq_process_host with the staging chunk forced to 1 MiB: 16 chunks through the ring of staging buffers, every buffer's
+    kernel stream used twice.  Output and filter state must equal the device-resident call (run in a subprocess: the chunk
+    size is read from the environment once per process)."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import numpy as np, torch
+        from dspi_b200 import api, workloads as W
+        fs, Cn, T = 96000.0, 4096, 1024
+        bq = api.compute_coefficients(W.eq_params_fast("B", Cn, fs=fs, seed=3), q28=False, fs=fs)
+        x = W.inputs_f32(Cn, T)
+        a = api.EqEngine("f32f", Cn); a.upload(bq)
+        buf = torch.from_numpy(x).cuda(); a.process_device(buf.data_ptr(), T, T); a.process_device(buf.data_ptr(), T, T); a.sync()
+        want, wst = buf.cpu().numpy(), a.download(); a.close()
+        b = api.EqEngine("f32f", Cn); b.upload(bq)
+        pin = api.PinnedBuffer((Cn, T), np.float32); pin.array[...] = x
+        b.process_host(pin.array); b.process_host(pin.array)
+        assert np.array_equal(pin.array.view(np.uint32), want.view(np.uint32)), "samples differ"
+        st = b.download()
+        for f in st.dtype.names: assert np.array_equal(st[f].view(np.uint8), wst[f].view(np.uint8)), f
+        assert b.launch_count >= 32, b.launch_count
+        b.close(); print("ok")
+    ''')
+    env = dict(os.environ, DSPI_HOST_CHUNK_MB="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
