@@ -390,7 +390,7 @@ def main():
             dt = float(t.item())
         e2e = {"value": float(Cn) * T * n_e2e * world / dt, "unit": "samples/s", "h2d_bytes_per_step": Cn * T * 4 * world,
                "d2h_bytes_per_step": Cn * T * 4 * world, "steps": n_e2e, "numa_node": numa_node,
-               "path": "dspi_eq_process_host: pinned host [C][T] -> channel-chunked cudaMemcpyAsync H2D / kernel / D2H on 3 streams"}
+               "path": "dspi_eq_process_host: pinned host [C][T] -> channel-chunked cudaMemcpyAsync H2D / kernel / D2H: copy-in stream, copy-out stream, a kernel stream per staging buffer (48 MiB chunks, ring of 8)"}
         pin.free()
 
     cpu = None

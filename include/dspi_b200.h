@@ -150,6 +150,7 @@ int dspi_eq_process_device(dspi_eq *e, void *d_samples, uint32_t T, uint32_t ld)
  * multiple of 64.  For callers that stream a large block through in pieces (dspi_b200/sharding.py pipelines NCCL transfers
  * against it).  Asynchronous on the engine's stream. */
 int dspi_eq_process_device_range(dspi_eq *e, void *d_rows, uint32_t T, uint32_t ld, uint32_t ch0, uint32_t n);
+/* Host block: staged through the device in 48 MiB channel chunks (DSPI_HOST_CHUNK_MB in the environment overrides). */
 int dspi_eq_process_host(dspi_eq *e, void *h_samples, uint32_t T);
 int dspi_eq_sync(dspi_eq *e);
 /* cudaStream_t of the engine (so callers can order their own work / events) */
