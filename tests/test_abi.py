@@ -132,3 +132,45 @@ def test_q28_chain_parameter_functions_match_the_reference(lib, refs):
             want = np.zeros((L.LOUD_STEPS, 2), L.LOUD_Q28)
             refs["q28"].lib.ref_loud_table(want.ctypes.data, ref_spl, inten, fs)
             assert np.array_equal(field_bits(api.loudness_table_q28(fs, ref_spl, inten)), field_bits(want))
+
+
+def test_multi_gpu_entry_points_reject_bad_arguments(lib):
+    """dspi_eqx_* / dspi_sg_* validate before they touch a device (runs without a GPU)."""
+    import ctypes as C
+    h = C.c_void_p()
+    dev = (C.c_int32 * 8)(0, 1, 2, 3, 4, 5, 6, 7)
+    assert lib.dspi_eqx_create(None, None) == -22
+    assert lib.dspi_eqx_create(C.byref(h), C.byref(api._EqxDesc(0, 1024, 10, 0, dev, 0))) == -22          # no device
+    assert lib.dspi_eqx_create(C.byref(h), C.byref(api._EqxDesc(0, 1024, 10, 9, dev, 0))) == -22          # more than DSPI_MAX_DEVICES
+    assert lib.dspi_eqx_create(C.byref(h), C.byref(api._EqxDesc(0, 0, 10, 2, dev, 0))) == -22             # no channels
+    twice = (C.c_int32 * 8)(0, 1, 0, 3, 4, 5, 6, 7)
+    assert lib.dspi_eqx_create(C.byref(h), C.byref(api._EqxDesc(0, 1024, 10, 3, twice, 0))) == -22
+    assert b"twice" in lib.dspi_last_error()
+    assert not h.value
+    lo, hi = C.c_uint32(), C.c_uint32()
+    assert lib.dspi_eqx_shard_range(1024, 0, 0, C.byref(lo), C.byref(hi)) == -22
+    assert lib.dspi_eqx_shard_range(1024, 2, 2, C.byref(lo), C.byref(hi)) == -22
+    assert lib.dspi_eqx_process_host(None, None, 16) == -22
+    assert lib.dspi_eqx_process_root(None, None, 16, 16) == -22
+    assert lib.dspi_sg_create(None, None, 0, None, 0, 1, 0) == -22
+    assert lib.dspi_sg_process(None, None, 64, 16, 0) == -22
+    assert lib.dspi_nccl_unique_id(None) == -22
+
+
+@pytest.mark.parametrize("total,world", [(64, 1), (64, 2), (65, 2), (1000, 3), (65536, 8), (524288, 8), (130, 8), (1, 4)])
+def test_shard_ranges_tile_the_channels_on_64_row_units(lib, total, world):
+    """dspi_eqx_shard_range (the one sharding rule of dspi_eqx_*, dspi_sg_* and dspi_b200/sharding.py): contiguous, complete,
+    every boundary but the last on a multiple of 64 channels, sizes differing by at most one unit."""
+    import ctypes as C
+    from dspi_b200 import sharding
+    edges = []
+    for k in range(world):
+        lo, hi = C.c_uint32(), C.c_uint32()
+        assert lib.dspi_eqx_shard_range(total, world, k, C.byref(lo), C.byref(hi)) == 0
+        edges.append((lo.value, hi.value))
+        assert (lo.value, hi.value) == tuple(sharding.shard_range(total, k, world))
+    assert edges[0][0] == 0 and edges[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+    assert all(lo % 64 == 0 for lo, _ in edges if lo < total)
+    units = [-(-(hi - lo) // 64) for lo, hi in edges]
+    assert max(units) - min(units) <= 1
