@@ -174,3 +174,25 @@ def test_shard_ranges_tile_the_channels_on_64_row_units(lib, total, world):
     assert all(lo % 64 == 0 for lo, _ in edges if lo < total)
     units = [-(-(hi - lo) // 64) for lo, hi in edges]
     assert max(units) - min(units) <= 1
+
+
+def test_chain_entry_points_reject_bad_arguments(lib):
+    """dspi_chain_* / dspi_chainq_* argument checks come before any device work (runs without a GPU)."""
+    import ctypes as C
+    h = C.c_void_p()
+    for create, good_arith in ((lib.dspi_chain_create, 0), (lib.dspi_chainq_create, 2)):
+        assert create(None, None) == -22
+        assert create(C.byref(h), C.byref(api._ChainDesc(2 - good_arith, 16, 10, 0, 96))) == -22            # the other engine's arithmetic
+        assert create(C.byref(h), C.byref(api._ChainDesc(good_arith, 0, 10, 0, 96))) == -22                 # no instances
+        assert create(C.byref(h), C.byref(api._ChainDesc(good_arith, 16, 10, 0, 0))) == -22                 # no frames
+        assert create(C.byref(h), C.byref(api._ChainDesc(good_arith, 16, 13, 0, 96))) == -22                # more bands than MAX_BANDS
+        assert not h.value
+    assert lib.dspi_chain_create(C.byref(h), C.byref(api._ChainDesc(0, 16, 7, 0, 96))) == -22                # the float chain runs channel_band_counts = 10
+    assert lib.dspi_chain_set_params(None, 0, 1, None) == -22
+    assert lib.dspi_chainq_set_params(None, 0, 1, None) == -22
+    assert lib.dspi_chain_set_dynamics_device(None, 0, 1, None, C.c_float(48000.0)) == -22
+    assert lib.dspi_chainq_set_dynamics_device(None, 0, 1, None, C.c_float(48000.0)) == -22
+    assert lib.dspi_chain_set_preset_mute(None, 0, 1, None, 48000) == -22
+    assert lib.dspi_chainq_set_preset_mute(None, 0, 1, None, 48000) == -22
+    assert lib.dspi_chain_state_export(None, None, 0) == -22
+    assert lib.dspi_chainq_state_export(None, None, 0) == -22
