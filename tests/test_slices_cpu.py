@@ -17,7 +17,7 @@ def plans(tmp_path_factory):
         pytest.skip("nvcc not on PATH")
     exe = str(tmp_path_factory.mktemp("slices") / "slices")
     subprocess.run(["nvcc", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "dspi_b200", "csrc"), "-o", exe,
-                    os.path.join(ROOT, "tests", "c_client", "slices.cu"), "-lcuda"], check=True, capture_output=True, timeout=600)
+                    os.path.join(ROOT, "tests", "c_client", "slices.cu")], check=True, capture_output=True, timeout=600)
     env = {k: v for k, v in os.environ.items() if k != "DSPI_UNIFORM_SLICES"}
     out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=60, env=env).stdout
     res = {}
